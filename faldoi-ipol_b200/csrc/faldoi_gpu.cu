@@ -1,0 +1,827 @@
+// libfaldoi_gpu.so -- C ABI (include/faldoi_gpu.h) over the sm_100a kernels.
+// Build: see faldoi-ipol_b200/build.py  (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false ...)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+
+#include "solver.h"
+#include "tv_kernels.cuh"
+#include "warp_kernels.cuh"
+#include "nltv_kernels.cuh"
+#include "occ_kernels.cuh"
+
+using namespace faldoi;
+
+static int occ_upload(faldoi_solver *s, int slot, const float *Im1, const float *u, const float *chi);
+static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs);
+static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs);
+static int up2d(faldoi_solver *s, float *dst_plane, const float *src);
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+namespace faldoi {
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+}  // namespace faldoi
+
+extern "C" const char *faldoi_last_error(void) { return g_err.c_str(); }
+
+extern "C" int faldoi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// parameters: init_params (src/utils_preprocess.cpp:37-157) + main()'s overrides
+// ---------------------------------------------------------------------------
+static void base_defaults(faldoi_params *p) {
+    // src/parameters.h:20-31 (double literals narrowed to float, as the reference's `params.x = PAR_...`)
+    p->lambda = 40;
+    p->theta = 0.3;
+    p->tau = 0.125;
+    p->beta = 0.025;
+    p->alpha = 0.0706776435878;
+    p->tau_u = 0.0739776273913;
+    p->tau_eta = 0.0839911992024;
+    p->tau_chi = 0.134077646787;
+    p->mu = 1.4058686732;
+    p->tol = 0.01;
+    p->warps = 5;
+}
+
+static int finish_params(int method, int glb_iters, faldoi_params *p) {
+    if (method < 0 || method > 8) {
+        set_error("unknown method id");
+        return FALDOI_ERR_ARG;
+    }
+    p->method = method;
+    // src/global_faldoi.cpp:2138-2156: methods 2-7 overwrite lambda/theta/tau after init_params
+    if (method == FALDOI_M_NLTVCSAD || method == FALDOI_M_NLTVCSAD_W) {
+        p->lambda = 0.85;
+        p->theta = 0.3;
+        p->tau = 0.1;
+    } else if (method == FALDOI_M_NLTVL1 || method == FALDOI_M_NLTVL1_W) {
+        p->lambda = 2.0;
+        p->theta = 0.3;
+        p->tau = 0.1;
+    } else if (method == FALDOI_M_TVCSAD || method == FALDOI_M_TVCSAD_W) {
+        p->lambda = 0.85;
+        p->theta = 0.3;
+        p->tau = 0.125;
+    }
+    // methods 0-7 loop to the compile-time MAX_ITERATIONS_GLOBAL; only method 8 reads -glb_iters
+    p->max_iters = (method == FALDOI_M_TVL1_OCC) ? glb_iters : 400;
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_default_params(int method, int glb_iters, faldoi_params *out) {
+    if (!out) return FALDOI_ERR_ARG;
+    base_defaults(out);
+    return finish_params(method, glb_iters, out);
+}
+
+extern "C" int faldoi_params_from_file(const char *path, int method, int glb_iters, faldoi_params *out) {
+    if (!out) return FALDOI_ERR_ARG;
+    base_defaults(out);
+    if (path && path[0]) {
+        std::ifstream in(path);
+        std::string line;
+        float v[9];
+        for (int i = 0; i < 9; i++) {
+            // the reference calls std::stof on each line and dies on a missing / short file
+            if (!std::getline(in, line)) {
+                set_error(std::string("parameter file missing or shorter than 9 lines: ") + path);
+                return FALDOI_ERR_ARG;
+            }
+            try {
+                v[i] = std::stof(line);
+            } catch (...) {
+                set_error(std::string("parameter file: not a number: ") + line);
+                return FALDOI_ERR_ARG;
+            }
+        }
+        const faldoi_params d = *out;
+        out->lambda = v[0] <= 0 ? d.lambda : v[0];
+        out->theta = v[1] <= 0 ? d.theta : v[1];
+        out->tau = (v[2] <= 0 || v[2] > 0.25) ? d.tau : v[2];
+        out->beta = v[3] <= 0 ? d.beta : v[3];
+        out->alpha = v[4] <= 0 ? d.alpha : v[4];
+        out->tau_u = (v[5] <= 0 || v[5] > 0.25) ? d.tau_u : v[5];
+        out->tau_eta = (v[6] <= 0 || v[6] > 0.25) ? d.tau_eta : v[6];
+        out->tau_chi = (v[7] <= 0 || v[7] > 0.25) ? d.tau_chi : v[7];
+        out->mu = v[8] <= 0 ? d.mu : v[8];
+    }
+    return finish_params(method, glb_iters, out);
+}
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+float *faldoi_solver::dmalloc(size_t nfloats) {
+    void *p = nullptr;
+    if (!cuda_ok(cudaMalloc(&p, nfloats * sizeof(float)), "cudaMalloc")) return nullptr;
+    if (!cuda_ok(cudaMemsetAsync(p, 0, nfloats * sizeof(float), stream), "cudaMemset")) return nullptr;
+    allocs.push_back(p);
+    return (float *)p;
+}
+
+int faldoi_solver::alloc_err(int max_iters) {
+    if (max_iters <= err_cap) return FALDOI_OK;
+    // (old arrays stay in `allocs` until destroy; growth happens at most a few times)
+    err_max = (unsigned *)dmalloc((size_t)B * max_iters);
+    err_sum = (double *)dmalloc((size_t)B * max_iters * 2);
+    if (!err_max || !err_sum) return FALDOI_ERR_MEM;
+    err_cap = max_iters;
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_solver_create(faldoi_solver **out, int device, int w, int h, int method, int batch) {
+    if (!out || w < 2 || h < 2 || batch < 1 || method < 0 || method > 8) {
+        set_error("faldoi_solver_create: bad argument");
+        return FALDOI_ERR_ARG;
+    }
+    int ndev = 0;
+    FALDOI_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_error("faldoi_solver_create: no such CUDA device");
+        return FALDOI_ERR_CUDA;
+    }
+    FALDOI_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FALDOI_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("libfaldoi_gpu is built for sm_100a only; device is ") + prop.name);
+        return FALDOI_ERR_CUDA;
+    }
+    faldoi_solver *s = new faldoi_solver();
+    s->device = device;
+    s->method = method;
+    s->B = batch;
+    s->g.w = w;
+    s->g.h = h;
+    s->g.pitch = (w + 31) / 32 * 32;
+    s->g.B = batch;
+    s->g.plane = (size_t)s->g.pitch * h;
+    const size_t P = s->g.plane, B = batch;
+    auto fail = [&](int code) {
+        faldoi_solver_destroy(s);
+        return code;
+    };
+    if (!cuda_ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(FALDOI_ERR_CUDA);
+    if (!cuda_ok(cudaEventCreate(&s->ev0), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&s->ev1), "cudaEventCreate"))
+        return fail(FALDOI_ERR_CUDA);
+
+#define ALLOC(ptr, n)                                  \
+    do {                                               \
+        (ptr) = s->dmalloc((size_t)(n));               \
+        if (!(ptr)) return fail(FALDOI_ERR_MEM);       \
+    } while (0)
+
+    ALLOC(s->I0, B * P);
+    ALLOC(s->I1, B * P);
+    ALLOC(s->I1x, B * P);
+    ALLOC(s->I1y, B * P);
+    ALLOC(s->packed, B * 3 * (size_t)w * h);
+    s->parity = (int *)s->dmalloc(B);
+    s->log_iters = (int *)s->dmalloc(B * FALDOI_MAX_WARPS);
+    s->log_err = s->dmalloc(B * FALDOI_MAX_WARPS);
+    if (!s->parity || !s->log_iters || !s->log_err) return fail(FALDOI_ERR_MEM);
+    if (s->alloc_err(400) != FALDOI_OK) return fail(FALDOI_ERR_MEM);
+
+    const Family fam = method_family(method);
+    if (fam == FAM_TV || fam == FAM_NLTV) {
+        s->set_stride = (size_t)ST_COUNT * B * P;
+        ALLOC(s->state, 2 * s->set_stride);
+        ALLOC(s->Ix, B * P);
+        ALLOC(s->Iy, B * P);
+        if (method_is_csad(method)) {
+            ALLOC(s->scale, B * P);
+            ALLOC(s->I1w, B * P);
+            ALLOC(s->bs, 48 * B * P);
+        } else {
+            ALLOC(s->rho_c, B * P);
+        }
+    }
+    if (fam == FAM_NLTV) {
+        ALLOC(s->lab, 3 * B * P);
+        ALLOC(s->wgt, (size_t)NL_SLOTS * B * P);
+        ALLOC(s->wt, B * P);
+        s->dual_set_stride = (size_t)2 * NL_SLOTS * B * P;
+        ALLOC(s->dual, 2 * s->dual_set_stride);
+    }
+    if (fam == FAM_OCC) {
+        ALLOC(s->occ, (size_t)OCC_PLANES * B * P);
+    }
+#undef ALLOC
+    if (!cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize")) return fail(FALDOI_ERR_CUDA);
+    *out = s;
+    return FALDOI_OK;
+}
+
+extern "C" void faldoi_solver_destroy(faldoi_solver *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int up2d(faldoi_solver *s, float *dst_plane, const float *src) {
+    FALDOI_CUDA(cudaMemcpy2DAsync(dst_plane, s->g.pitch * sizeof(float), src, s->g.w * sizeof(float),
+                                  s->g.w * sizeof(float), s->g.h, cudaMemcpyHostToDevice, s->stream));
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0, const float *I1, const float *Im1,
+                                    const float *lab, const float *u, const float *chi) {
+    if (!s || slot < 0 || slot >= s->B || !I0 || !I1 || !u) {
+        set_error("faldoi_solver_upload: bad argument");
+        return FALDOI_ERR_ARG;
+    }
+    const Family fam = method_family(s->method);
+    if ((fam == FAM_NLTV && !lab) || (fam == FAM_OCC && (!Im1 || !chi))) {
+        set_error("faldoi_solver_upload: this method needs lab (NLTV) / Im1 and chi (occlusions)");
+        return FALDOI_ERR_ARG;
+    }
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    const size_t P = s->g.plane, B = s->B, n = (size_t)s->g.w * s->g.h;
+    int rc;
+    if ((rc = up2d(s, s->I0 + slot * P, I0))) return rc;
+    if ((rc = up2d(s, s->I1 + slot * P, I1))) return rc;
+    if (fam == FAM_TV || fam == FAM_NLTV) {
+        // flow into set 0, parity 0, duals zeroed (src/global_faldoi.cpp:2116-2121; NLTV sc = 0 :1027)
+        float *set0 = s->state;
+        if ((rc = up2d(s, set0 + (ST_U1 * B + slot) * P, u))) return rc;
+        if ((rc = up2d(s, set0 + (ST_U2 * B + slot) * P, u + n))) return rc;
+        for (int k = ST_XI11; k <= ST_XI22; k++)
+            FALDOI_CUDA(cudaMemsetAsync(set0 + (k * B + slot) * P, 0, P * sizeof(float), s->stream));
+        FALDOI_CUDA(cudaMemsetAsync(s->parity + slot, 0, sizeof(int), s->stream));
+    }
+    if (fam == FAM_NLTV) {
+        for (int c = 0; c < 3; c++)
+            if ((rc = up2d(s, s->lab + (c * B + slot) * P, lab + c * n))) return rc;
+        for (int k = 0; k < 2 * NL_SLOTS; k++)
+            FALDOI_CUDA(cudaMemsetAsync(s->dual + (k * B + slot) * P, 0, P * sizeof(float), s->stream));
+    }
+    if (fam == FAM_OCC) {
+        if ((rc = occ_upload(s, slot, Im1, u, chi))) return rc;
+    }
+    return FALDOI_OK;
+}
+
+// ---------------------------------------------------------------------------
+// end-of-warp bookkeeping: iterations run, last error, ping-pong parity
+// ---------------------------------------------------------------------------
+__global__ void finalize_warp_kernel(const unsigned *err_max, const double *err_sum, int use_sum, int always_all,
+                                     int *parity, int *log_iters, float *log_err, int max_iters, float tol2,
+                                     float npix, int warp_idx, int npairs) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= npairs) return;
+    int n = 0;
+    float e = INFINITY;
+    while (n < max_iters) {
+        e = use_sum ? (float)err_sum[(size_t)b * max_iters + n] / npix : __uint_as_float(err_max[(size_t)b * max_iters + n]);
+        n++;
+        if (!always_all && !(e > tol2)) break;
+    }
+    if (parity) parity[b] = (parity[b] + n) & 1;
+    log_iters[b * FALDOI_MAX_WARPS + warp_idx] = n;
+    log_err[b * FALDOI_MAX_WARPS + warp_idx] = e;
+}
+
+__global__ void export_flow_kernel(const float *state, size_t set_stride, const int *parity, float *packed, Geo g) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= g.w || y >= g.h) return;
+    const float *set = state + (size_t)parity[b] * set_stride + (size_t)b * g.plane;
+    const size_t ks = (size_t)g.B * g.plane, n = (size_t)g.w * g.h;
+    float *o = packed + (size_t)b * 3 * n;
+    o[(size_t)y * g.w + x] = set[ST_U1 * ks + (size_t)y * g.pitch + x];
+    o[n + (size_t)y * g.w + x] = set[ST_U2 * ks + (size_t)y * g.pitch + x];
+}
+
+static dim3 grid2d(const Geo &g, dim3 block, int npairs) {
+    return dim3((g.w + block.x - 1) / block.x, (g.h + block.y - 1) / block.y, npairs);
+}
+
+template <int DATA>
+static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
+    const dim3 block(32, 8);
+    const int cols = (s->g.pitch + 127) / 128;
+    if (R == 4)
+        tv_iter_kernel<4, DATA><<<dim3(cols, (s->g.h + 31) / 32, npairs), block, 0, s->stream>>>(a, it);
+    else if (R == 2)
+        tv_iter_kernel<2, DATA><<<dim3(cols, (s->g.h + 15) / 16, npairs), block, 0, s->stream>>>(a, it);
+    else
+        tv_iter_kernel<1, DATA><<<dim3(cols, (s->g.h + 7) / 8, npairs), block, 0, s->stream>>>(a, it);
+}
+
+// rows per thread: as many as keep >= ~2 waves of 8-warp CTAs on 148 SMs
+static int pick_rows(const Geo &g, int npairs) {
+    const long warps1 = (long)((g.pitch + 127) / 128) * g.h * npairs;  // warps at R = 1
+    if (warps1 / 4 >= 148L * 64) return 4;
+    if (warps1 / 2 >= 148L * 64) return 2;
+    return 1;
+}
+
+static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
+    const Geo g = s->g;
+    const bool csad = method_is_csad(s->method);
+    const dim3 blk(32, 8);
+    centered_gradient_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->I1, s->I1x, s->I1y, g);
+    s->launches++;
+    const size_t ks = (size_t)g.B * g.plane;
+    TvArgs a{};
+    a.state = s->state;
+    a.set_stride = s->set_stride;
+    a.Ix = s->Ix;
+    a.Iy = s->Iy;
+    a.rho_c = s->rho_c;
+    a.scale = s->scale;
+    a.bs = s->bs;
+    a.err_max = s->err_max;
+    a.err_sum = s->err_sum;
+    a.parity = s->parity;
+    a.g = g;
+    a.max_iters = p->max_iters;
+    a.tau = p->tau;
+    a.theta = p->theta;
+    a.l_t = p->lambda * p->theta;
+    a.tol2 = p->tol * p->tol;
+    const int R = pick_rows(g, npairs);
+    for (int wp = 0; wp < p->warps; wp++) {
+        if (csad)
+            FALDOI_CUDA(cudaMemsetAsync(s->err_sum, 0, (size_t)g.B * p->max_iters * sizeof(double), s->stream));
+        else
+            FALDOI_CUDA(cudaMemsetAsync(s->err_max, 0, (size_t)g.B * p->max_iters * sizeof(unsigned), s->stream));
+        WarpArgs wa{};
+        wa.I0 = s->I0;
+        wa.I1 = s->I1;
+        wa.I1x = s->I1x;
+        wa.I1y = s->I1y;
+        wa.u1 = s->state + ST_U1 * ks;
+        wa.u2 = s->state + ST_U2 * ks;
+        wa.ub1 = s->state + ST_UB1 * ks;
+        wa.ub2 = s->state + ST_UB2 * ks;
+        wa.Ix = s->Ix;
+        wa.Iy = s->Iy;
+        wa.rho_c = csad ? nullptr : s->rho_c;
+        wa.I1w = csad ? s->I1w : nullptr;
+        wa.parity = s->parity;
+        wa.set_stride = s->set_stride;
+        wa.g = g;
+        warp_constants_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(wa);
+        s->launches++;
+        if (csad) {
+            CsadArgs ca{};
+            ca.I0 = s->I0;
+            ca.I1w = s->I1w;
+            ca.Ix = s->Ix;
+            ca.Iy = s->Iy;
+            ca.u1 = wa.u1;
+            ca.u2 = wa.u2;
+            ca.parity = s->parity;
+            ca.set_stride = s->set_stride;
+            ca.scale = s->scale;
+            ca.bs = s->bs;
+            ca.g = g;
+            ca.hyp = 1;
+            const dim3 cb(32, 4);
+            csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
+            s->launches++;
+        }
+        for (int it = 0; it < p->max_iters; it++) {
+            if (csad)
+                launch_tv_iter<DATA_CSAD>(s, a, it, npairs, R);
+            else
+                launch_tv_iter<DATA_TVL1>(s, a, it, npairs, R);
+        }
+        s->launches += p->max_iters;
+        finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, 0, s->parity,
+                                                                       s->log_iters, s->log_err, p->max_iters, a.tol2,
+                                                                       (float)(g.w * g.h), wp, npairs);
+        s->launches++;
+    }
+    export_flow_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->state, s->set_stride, s->parity, s->packed, g);
+    s->launches++;
+    FALDOI_CUDA(cudaGetLastError());
+    return FALDOI_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// NLTV family (methods 2,3,6,7)
+// ---------------------------------------------------------------------------
+static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
+    const Geo g = s->g;
+    const bool csad = method_is_csad(s->method);
+    const dim3 blk(32, 8);
+    const size_t ks = (size_t)g.B * g.plane;
+    NlOffsets offs;
+    for (int sl = 0; sl < NL_SLOTS; sl++) {
+        int k, l;
+        nl_slot_offset(sl, k, l);
+        // get_wspatial_2 (src/global_faldoi.cpp:943-952): difS = hypot(l,k) (double) stored as float
+        const float difS = (float)hypot((double)l, (double)k);
+        offs.ws[sl] = expf(-difS / 2.f);
+    }
+    nltv_init_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->lab, s->wgt, s->wt, offs, g);
+    centered_gradient_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->I1, s->I1x, s->I1y, g);
+    s->launches += 2;
+    NlArgs a{};
+    a.state = s->state;
+    a.set_stride = s->set_stride;
+    a.dual = s->dual;
+    a.dual_set_stride = s->dual_set_stride;
+    a.wgt = s->wgt;
+    a.wt = s->wt;
+    a.Ix = s->Ix;
+    a.Iy = s->Iy;
+    a.rho_c = s->rho_c;
+    a.scale = s->scale;
+    a.bs = s->bs;
+    a.err_sum = s->err_sum;
+    a.g = g;
+    a.max_iters = p->max_iters;
+    a.tau = p->tau;
+    a.theta = p->theta;
+    a.l_t = p->lambda * p->theta;
+    int base_parity = 0;  // every pair runs all max_iters iterations: one parity for the batch
+    FALDOI_CUDA(cudaMemsetAsync(s->parity, 0, (size_t)g.B * sizeof(int), s->stream));
+    for (int wp = 0; wp < p->warps; wp++) {
+        FALDOI_CUDA(cudaMemsetAsync(s->err_sum, 0, (size_t)g.B * p->max_iters * sizeof(double), s->stream));
+        WarpArgs wa{};
+        wa.I0 = s->I0;
+        wa.I1 = s->I1;
+        wa.I1x = s->I1x;
+        wa.I1y = s->I1y;
+        wa.u1 = s->state + ST_U1 * ks;
+        wa.u2 = s->state + ST_U2 * ks;
+        wa.ub1 = s->state + ST_UB1 * ks;
+        wa.ub2 = s->state + ST_UB2 * ks;
+        wa.Ix = s->Ix;
+        wa.Iy = s->Iy;
+        wa.rho_c = csad ? nullptr : s->rho_c;
+        wa.I1w = csad ? s->I1w : nullptr;
+        wa.parity = s->parity;
+        wa.set_stride = s->set_stride;
+        wa.g = g;
+        warp_constants_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(wa);
+        s->launches++;
+        if (csad) {
+            CsadArgs ca{};
+            ca.I0 = s->I0;
+            ca.I1w = s->I1w;
+            ca.Ix = s->Ix;
+            ca.Iy = s->Iy;
+            ca.u1 = wa.u1;
+            ca.u2 = wa.u2;
+            ca.parity = s->parity;
+            ca.set_stride = s->set_stride;
+            ca.scale = s->scale;
+            ca.bs = s->bs;
+            ca.g = g;
+            ca.hyp = 0;
+            const dim3 cb(32, 4);
+            csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
+            s->launches++;
+        }
+        for (int it = 0; it < p->max_iters; it++) {
+            if (csad)
+                nltv_iter_kernel<DATA_CSAD><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
+            else
+                nltv_iter_kernel<DATA_TVL1><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
+        }
+        s->launches += p->max_iters;
+        finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, 1, 1, s->parity, s->log_iters,
+                                                                       s->log_err, p->max_iters, 0.f, (float)(g.w * g.h),
+                                                                       wp, npairs);
+        s->launches++;
+        base_parity = (base_parity + p->max_iters) & 1;
+    }
+    export_flow_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->state, s->set_stride, s->parity, s->packed, g);
+    s->launches++;
+    FALDOI_CUDA(cudaGetLastError());
+    return FALDOI_OK;
+}
+
+// ---------------------------------------------------------------------------
+// TVL2 + occlusions (method 8)
+// ---------------------------------------------------------------------------
+static int occ_upload(faldoi_solver *s, int slot, const float *Im1, const float *u, const float *chi) {
+    const size_t P = s->g.plane, B = s->B, n = (size_t)s->g.w * s->g.h;
+    int rc;
+    if ((rc = up2d(s, s->occ + (OC_IM1 * B + slot) * P, Im1))) return rc;
+    if ((rc = up2d(s, s->occ + (OC_U1 * B + slot) * P, u))) return rc;
+    if ((rc = up2d(s, s->occ + (OC_U2 * B + slot) * P, u + n))) return rc;
+    if ((rc = up2d(s, s->occ + (OC_CHI0 * B + slot) * P, chi))) return rc;
+    // eta = 0 at entry (target definition; the reference never initialises it)
+    FALDOI_CUDA(cudaMemsetAsync(s->occ + (OC_ETA0 * B + slot) * P, 0, P * sizeof(float), s->stream));
+    FALDOI_CUDA(cudaMemsetAsync(s->occ + ((OC_ETA0 + 1) * B + slot) * P, 0, P * sizeof(float), s->stream));
+    return FALDOI_OK;
+}
+
+static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
+    const Geo g = s->g;
+    const dim3 blk(32, 8);
+    const dim3 grd = grid2d(g, blk, npairs);
+    OccArgs a{};
+    a.pl = s->occ;
+    a.I0 = s->I0;
+    a.I1 = s->I1;
+    a.I1x = s->I1x;
+    a.I1y = s->I1y;
+    a.err_max = s->err_max;
+    a.g = g;
+    a.max_iters = p->max_iters;
+    a.lambda = p->lambda;
+    a.theta = p->theta;
+    a.beta = p->beta;
+    a.alpha = p->alpha;
+    a.tau_theta = p->tau_u / p->theta;
+    a.mu = p->mu;
+    a.tau_eta = p->tau_eta;
+    a.tau_chi = p->tau_chi;
+    a.l_t = p->lambda * p->theta;
+    a.tol2 = p->tol * p->tol;
+    centered_gradient_kernel<<<grd, blk, 0, s->stream>>>(s->I1, s->I1x, s->I1y, g);
+    occ_init_kernel<<<grd, blk, 0, s->stream>>>(a);
+    s->launches += 2;
+    for (int wp = 0; wp < p->warps; wp++) {
+        FALDOI_CUDA(cudaMemsetAsync(s->err_max, 0, (size_t)g.B * p->max_iters * sizeof(unsigned), s->stream));
+        occ_warp_kernel<<<grd, blk, 0, s->stream>>>(a);
+        s->launches++;
+        for (int it = 0; it < p->max_iters; it++) {
+            occ_v_kernel<<<grd, blk, 0, s->stream>>>(a, it);
+            for (int k = 0; k < 24; k++) occ_xi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1);
+            occ_u_kernel<<<grd, blk, 0, s->stream>>>(a, it);
+            for (int k = 0; k < 24; k++) occ_chi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1, k == 23);
+            s->launches += 50;
+        }
+        finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, 0, 0, nullptr, s->log_iters,
+                                                                       s->log_err, p->max_iters, a.tol2, (float)(g.w * g.h),
+                                                                       wp, npairs);
+        s->launches++;
+    }
+    occ_export_kernel<<<grd, blk, 0, s->stream>>>(a, s->packed);
+    s->launches++;
+    FALDOI_CUDA(cudaGetLastError());
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_solver_run(faldoi_solver *s, const faldoi_params *p, int npairs) {
+    if (!s || !p || npairs < 1 || npairs > s->B || p->warps < 0 || p->warps > FALDOI_MAX_WARPS || p->max_iters < 0) {
+        set_error("faldoi_solver_run: bad argument");
+        return FALDOI_ERR_ARG;
+    }
+    if (method_family(p->method) != method_family(s->method) || method_is_csad(p->method) != method_is_csad(s->method)) {
+        set_error("faldoi_solver_run: params.method does not match the handle's method family");
+        return FALDOI_ERR_ARG;
+    }
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    if (s->alloc_err(p->max_iters > 0 ? p->max_iters : 1) != FALDOI_OK) return FALDOI_ERR_MEM;
+    s->launches = 0;
+    FALDOI_CUDA(cudaMemsetAsync(s->log_iters, 0, (size_t)s->B * FALDOI_MAX_WARPS * sizeof(int), s->stream));
+    FALDOI_CUDA(cudaEventRecord(s->ev0, s->stream));
+    int rc;
+    switch (method_family(s->method)) {
+        case FAM_TV: rc = run_tv(s, p, npairs); break;
+        case FAM_NLTV: rc = run_nltv(s, p, npairs); break;
+        default: rc = run_occ(s, p, npairs); break;
+    }
+    if (rc != FALDOI_OK) return rc;
+    FALDOI_CUDA(cudaEventRecord(s->ev1, s->stream));
+    s->ran = true;
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_solver_sync(faldoi_solver *s) {
+    if (!s) return FALDOI_ERR_ARG;
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    FALDOI_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->ran) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_ms = ms;
+    }
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_solver_download(faldoi_solver *s, int slot, float *u, float *chi, faldoi_log *log) {
+    if (!s || slot < 0 || slot >= s->B || !u) {
+        set_error("faldoi_solver_download: bad argument");
+        return FALDOI_ERR_ARG;
+    }
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->g.w * s->g.h;
+    FALDOI_CUDA(cudaMemcpyAsync(u, s->packed + (size_t)slot * 3 * n, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (chi && s->method == FALDOI_M_TVL1_OCC)
+        FALDOI_CUDA(cudaMemcpyAsync(chi, s->packed + (size_t)slot * 3 * n + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                    s->stream));
+    if (log) {
+        FALDOI_CUDA(cudaMemcpyAsync(log->iters, s->log_iters + slot * FALDOI_MAX_WARPS, sizeof(log->iters),
+                                    cudaMemcpyDeviceToHost, s->stream));
+        FALDOI_CUDA(cudaMemcpyAsync(log->err, s->log_err + slot * FALDOI_MAX_WARPS, sizeof(log->err),
+                                    cudaMemcpyDeviceToHost, s->stream));
+    }
+    return faldoi_solver_sync(s);
+}
+
+extern "C" float faldoi_solver_last_run_ms(faldoi_solver *s) { return s ? s->last_ms : -1.f; }
+extern "C" long long faldoi_solver_last_launches(faldoi_solver *s) { return s ? s->launches : -1; }
+extern "C" void *faldoi_solver_stream(faldoi_solver *s) { return s ? (void *)s->stream : nullptr; }
+extern "C" float *faldoi_solver_device_flow(faldoi_solver *s, int slot, int *pitch_floats) {
+    if (!s || slot < 0 || slot >= s->B) return nullptr;
+    if (pitch_floats) *pitch_floats = s->g.w;
+    return s->packed + (size_t)slot * 3 * s->g.w * s->g.h;
+}
+
+// ---------------------------------------------------------------------------
+// one-call host entry and the per-solver mirrors
+// ---------------------------------------------------------------------------
+namespace {
+struct CacheKey {
+    int device, w, h, method;
+};
+std::mutex g_cache_mu;
+faldoi_solver *g_cached = nullptr;
+CacheKey g_cached_key{-1, 0, 0, -1};
+}  // namespace
+
+// A single-pair handle is kept alive between calls with the same (device, w, h,
+// method) so a sequence of pairs does not pay cudaMalloc per call.
+static int cached_solver(int device, int w, int h, int method, faldoi_solver **out) {
+    if (g_cached && g_cached_key.device == device && g_cached_key.w == w && g_cached_key.h == h &&
+        g_cached_key.method == method) {
+        *out = g_cached;
+        return FALDOI_OK;
+    }
+    if (g_cached) {
+        faldoi_solver_destroy(g_cached);
+        g_cached = nullptr;
+    }
+    int rc = faldoi_solver_create(&g_cached, device, w, h, method, 1);
+    if (rc != FALDOI_OK) {
+        g_cached = nullptr;
+        return rc;
+    }
+    g_cached_key = CacheKey{device, w, h, method};
+    *out = g_cached;
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_global_solve(int device, const faldoi_params *p, int w, int h, const float *I0, const float *I1,
+                                   const float *Im1, const float *lab, float *u, float *chi, faldoi_log *log) {
+    if (!p || !I0 || !I1 || !u) {
+        set_error("faldoi_global_solve: null argument");
+        return FALDOI_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    faldoi_solver *s = nullptr;
+    int rc = cached_solver(device, w, h, p->method, &s);
+    if (rc != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_upload(s, 0, I0, I1, Im1, lab, u, chi)) != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_run(s, p, 1)) != FALDOI_OK) return rc;
+    return faldoi_solver_download(s, 0, u, chi, log);
+}
+
+static void print_log(const faldoi_params &p, const faldoi_log &log, FILE *f, const char *fmt) {
+    for (int k = 0; k < p.warps; k++) fprintf(f, fmt, k, log.iters[k], log.err[k]);
+}
+
+static int solve_split(const faldoi_params &p, int nx, int ny, const float *I0, const float *I1, const float *Im1,
+                       const float *lab, float *u1, float *u2, float *chi, int verbose, FILE *vf, const char *fmt) {
+    const size_t n = (size_t)nx * ny;
+    std::vector<float> u(2 * n);
+    memcpy(u.data(), u1, n * sizeof(float));
+    memcpy(u.data() + n, u2, n * sizeof(float));
+    faldoi_log log{};
+    int rc = faldoi_global_solve(0, &p, nx, ny, I0, I1, Im1, lab, u.data(), chi, &log);
+    if (rc != FALDOI_OK) return rc;
+    memcpy(u1, u.data(), n * sizeof(float));
+    memcpy(u2, u.data() + n, n * sizeof(float));
+    if (verbose) print_log(p, log, vf, fmt);
+    return FALDOI_OK;
+}
+
+// The reference's xi arguments are caller-owned scratch that main() zeroes right
+// before the call (src/global_faldoi.cpp:2116-2121) and never reads afterwards;
+// the GPU keeps the duals in HBM, so xi11..xi22 are accepted and left untouched.
+extern "C" int faldoi_tvl2OF(const float *I0, float *I1, float *u1, float *u2, float *, float *, float *, float *,
+                             float lambda, float theta, float tau, float tol_OF, int nx, int ny, int warps,
+                             int verbose) {
+    faldoi_params p;
+    faldoi_default_params(FALDOI_M_TVL1, 400, &p);
+    p.lambda = lambda, p.theta = theta, p.tau = tau, p.tol = tol_OF, p.warps = warps;
+    return solve_split(p, nx, ny, I0, I1, nullptr, nullptr, u1, u2, nullptr, verbose, stderr,
+                       "Warping: %d,Iter: %d Error: %f\n");
+}
+
+extern "C" int faldoi_tvcsad_PD(const float *I0, float *I1, float *, float *, float *, float *, float lambda,
+                                float theta, float tau, float tol_OF, int nx, int ny, int warps, int verbose,
+                                float *u1, float *u2) {
+    faldoi_params p;
+    faldoi_default_params(FALDOI_M_TVCSAD, 400, &p);
+    p.lambda = lambda, p.theta = theta, p.tau = tau, p.tol = tol_OF, p.warps = warps;
+    return solve_split(p, nx, ny, I0, I1, nullptr, nullptr, u1, u2, nullptr, verbose, stderr,
+                       "Warping: %d,Iter: %d Error: %f\n");
+}
+
+extern "C" int faldoi_nltvl1_PD(const float *I0, float *I1, float *a, int pd, float lambda, float theta, float tau,
+                                int w, int h, int warps, int verbose, float *u1, float *u2) {
+    if (pd != 3) {
+        set_error("NLTV needs the 3-channel Lab image (pd == 3)");
+        return FALDOI_ERR_ARG;
+    }
+    faldoi_params p;
+    faldoi_default_params(FALDOI_M_NLTVL1, 400, &p);
+    p.lambda = lambda, p.theta = theta, p.tau = tau, p.warps = warps;
+    return solve_split(p, w, h, I0, I1, nullptr, a, u1, u2, nullptr, verbose, stdout, "Warping: %d,Iter: %d Error: %f\n");
+}
+
+extern "C" int faldoi_nltvcsad_PD(const float *I0, float *I1, float *a, int pd, float lambda, float theta, float tau,
+                                  int w, int h, int warps, int verbose, float *u1, float *u2) {
+    if (pd != 3) {
+        set_error("NLTV needs the 3-channel Lab image (pd == 3)");
+        return FALDOI_ERR_ARG;
+    }
+    faldoi_params p;
+    faldoi_default_params(FALDOI_M_NLTVCSAD, 400, &p);
+    p.lambda = lambda, p.theta = theta, p.tau = tau, p.warps = warps;
+    return solve_split(p, w, h, I0, I1, nullptr, a, u1, u2, nullptr, verbose, stdout, "Warping: %d,Iter: %d Error: %f\n");
+}
+
+extern "C" int faldoi_guided_tvl2coupled_occ(const float *I0, const float *I1, const float *I_1, float *u1, float *u2,
+                                             float *chi, const faldoi_params *p, int nx, int ny, int verbose) {
+    if (!p || p->method != FALDOI_M_TVL1_OCC) {
+        set_error("faldoi_guided_tvl2coupled_occ: params.method must be 8");
+        return FALDOI_ERR_ARG;
+    }
+    return solve_split(*p, nx, ny, I0, I1, I_1, nullptr, u1, u2, chi, verbose, stdout,
+                       "Warping: %d, Iter: %d Error: %f\n");
+}
+
+// ---------------------------------------------------------------------------
+// standalone primitives on host arrays
+// ---------------------------------------------------------------------------
+namespace {
+struct Scratch {
+    std::vector<float *> d;
+    ~Scratch() {
+        for (float *p : d) cudaFree(p);
+    }
+    float *get(size_t n) {
+        float *p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) return nullptr;
+        d.push_back(p);
+        return p;
+    }
+};
+}  // namespace
+
+extern "C" int faldoi_centered_gradient(int device, const float *in, float *dx, float *dy, int nx, int ny) {
+    if (!in || !dx || !dy || nx < 2 || ny < 2) return FALDOI_ERR_ARG;
+    FALDOI_CUDA(cudaSetDevice(device));
+    Geo g{nx, ny, nx, 1, (size_t)nx * ny};
+    Scratch sc;
+    float *d_in = sc.get(g.plane), *d_dx = sc.get(g.plane), *d_dy = sc.get(g.plane);
+    if (!d_in || !d_dx || !d_dy) return FALDOI_ERR_MEM;
+    FALDOI_CUDA(cudaMemcpy(d_in, in, g.plane * sizeof(float), cudaMemcpyHostToDevice));
+    const dim3 blk(32, 8);
+    centered_gradient_kernel<<<grid2d(g, blk, 1), blk>>>(d_in, d_dx, d_dy, g);
+    FALDOI_CUDA(cudaGetLastError());
+    FALDOI_CUDA(cudaMemcpy(dx, d_dx, g.plane * sizeof(float), cudaMemcpyDeviceToHost));
+    FALDOI_CUDA(cudaMemcpy(dy, d_dy, g.plane * sizeof(float), cudaMemcpyDeviceToHost));
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_bicubic_warp(int device, const float *in, const float *u, const float *v, float *out, int nx,
+                                   int ny, int border_out) {
+    if (!in || !u || !v || !out || nx < 1 || ny < 1) return FALDOI_ERR_ARG;
+    FALDOI_CUDA(cudaSetDevice(device));
+    Geo g{nx, ny, nx, 1, (size_t)nx * ny};
+    Scratch sc;
+    float *d_in = sc.get(g.plane), *d_u = sc.get(g.plane), *d_v = sc.get(g.plane), *d_o = sc.get(g.plane);
+    if (!d_in || !d_u || !d_v || !d_o) return FALDOI_ERR_MEM;
+    FALDOI_CUDA(cudaMemcpy(d_in, in, g.plane * sizeof(float), cudaMemcpyHostToDevice));
+    FALDOI_CUDA(cudaMemcpy(d_u, u, g.plane * sizeof(float), cudaMemcpyHostToDevice));
+    FALDOI_CUDA(cudaMemcpy(d_v, v, g.plane * sizeof(float), cudaMemcpyHostToDevice));
+    const dim3 blk(32, 8);
+    bicubic_warp_kernel<<<grid2d(g, blk, 1), blk>>>(d_in, d_u, d_v, d_o, 1.f, border_out, g);
+    FALDOI_CUDA(cudaGetLastError());
+    FALDOI_CUDA(cudaMemcpy(out, d_o, g.plane * sizeof(float), cudaMemcpyDeviceToHost));
+    return FALDOI_OK;
+}

@@ -1,0 +1,322 @@
+// TVL2 + occlusion model (method 8): guided_tvl2coupled_occ
+// src/tvl2_model_occ.cpp:492-779 with the patch = whole image, GLOBAL_STEP.
+//
+// One outer iteration = v-update, 24 Chambolle sweeps for xi (:340-392) + final
+// divergence and u-update (:394-406, :726-751), 24 primal-dual sweeps for chi
+// (:431-474) and the hard threshold (:476-483).  The reference materialises
+// g*xi, div(g*xi), vi, grad(vi), g*eta, div(g*eta), chix, chiy as planes in
+// every sweep; here each sweep is ONE stencil kernel that recomputes those
+// intermediates from the radius-1 neighbourhood, so a xi sweep moves 9 planes
+// in / 4 out and a chi sweep 6 in / 3 out.
+//
+// Target definition: eta1 = eta2 = 0 and div_u = 0 at entry -- the
+// reference reads them uninitialised on this path.
+#pragma once
+#include "common.cuh"
+#include "warp_kernels.cuh"
+
+namespace faldoi {
+
+enum {
+    OC_IM1 = 0, OC_JX, OC_JY, OC_G, OC_UBA1, OC_UBA2, OC_I1WX, OC_I1WY, OC_JWX, OC_JWY, OC_RHO_C1, OC_RHO_C_1,
+    OC_U1, OC_U2, OC_V1, OC_V2, OC_K1, OC_K2, OC_F, OC_GG,
+    OC_XI0,            // 4 planes, set 0
+    OC_XI1 = OC_XI0 + 4,   // 4 planes, set 1
+    OC_ETA0 = OC_XI1 + 4,  // 2 planes, set 0
+    OC_ETA1 = OC_ETA0 + 2,
+    OC_CHI0 = OC_ETA1 + 2,
+    OC_CHI1,
+    OCC_PLANES
+};
+
+struct OccArgs {
+    float *pl;            // [OCC_PLANES][B]
+    const float *I0, *I1, *I1x, *I1y;
+    unsigned *err_max;    // [B][max_iters]
+    Geo g;
+    int max_iters;
+    float lambda, theta, beta, alpha, tau_theta, mu, tau_eta, tau_chi, l_t, tol2;
+};
+
+__device__ __forceinline__ float *occ_plane(const OccArgs &a, int kind, int b) {
+    return a.pl + ((size_t)kind * a.g.B + b) * a.g.plane;
+}
+
+__device__ __forceinline__ bool occ_active(const OccArgs &a, int b, int it) {
+    if (it == 0) return true;
+    return __uint_as_float(a.err_max[(size_t)b * a.max_iters + it - 1]) > a.tol2;
+}
+
+// once per run: gradients of I-1, weight g = 1/(1+0.05*|grad I0|) (init_weight
+// src/utils.cpp:838-852), frozen backward flow u_ba = -u (:597-598), xi = 0
+__global__ void __launch_bounds__(256) occ_init_kernel(OccArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    if (x >= w || y >= h) return;
+    const int p = y * pitch + x;
+    const int xr = (x < w - 1) ? p + 1 : p, xl = (x > 0) ? p - 1 : p;
+    const int yd = (y < h - 1) ? p + pitch : p, yu = (y > 0) ? p - pitch : p;
+    const float *J = occ_plane(a, OC_IM1, b);
+    occ_plane(a, OC_JX, b)[p] = (float)(0.5 * (J[xr] - J[xl]));
+    occ_plane(a, OC_JY, b)[p] = (float)(0.5 * (J[yd] - J[yu]));
+    const float *I0 = a.I0 + (size_t)b * a.g.plane;
+    const float i0x = (float)(0.5 * (I0[xr] - I0[xl])), i0y = (float)(0.5 * (I0[yd] - I0[yu]));
+    const float gr = sqrtf(i0x * i0x + i0y * i0y);
+    const float gamma = 0.05f;
+    occ_plane(a, OC_G, b)[p] = 1 / (1 + gamma * gr);
+    occ_plane(a, OC_UBA1, b)[p] = -occ_plane(a, OC_U1, b)[p];
+    occ_plane(a, OC_UBA2, b)[p] = -occ_plane(a, OC_U2, b)[p];
+#pragma unroll
+    for (int k = 0; k < 4; k++) occ_plane(a, OC_XI0 + k, b)[p] = 0.f;
+}
+
+// per warp: 6 bicubic warps with border_out = false (:616-623) + constants (:628-648)
+__global__ void __launch_bounds__(256) occ_warp_kernel(OccArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    if (x >= w || y >= h) return;
+    const int p = y * pitch + x;
+    const size_t off = (size_t)b * a.g.plane;
+    const float u1 = occ_plane(a, OC_U1, b)[p], u2 = occ_plane(a, OC_U2, b)[p];
+    const float i0 = a.I0[off + p];
+    {
+        const Taps t = make_taps(x + u1, y + u2, w, h);
+        const float iw = bicubic_sample(a.I1 + off, t, pitch);
+        const float ix = bicubic_sample(a.I1x + off, t, pitch);
+        const float iy = bicubic_sample(a.I1y + off, t, pitch);
+        occ_plane(a, OC_I1WX, b)[p] = ix;
+        occ_plane(a, OC_I1WY, b)[p] = iy;
+        occ_plane(a, OC_RHO_C1, b)[p] = iw - ix * u1 - iy * u2 - i0;
+    }
+    {
+        const float ub1 = occ_plane(a, OC_UBA1, b)[p], ub2 = occ_plane(a, OC_UBA2, b)[p];
+        const Taps t = make_taps(x + ub1, y + ub2, w, h);
+        const float jw = bicubic_sample(occ_plane(a, OC_IM1, b), t, pitch);
+        const float jx = bicubic_sample(occ_plane(a, OC_JX, b), t, pitch);
+        const float jy = bicubic_sample(occ_plane(a, OC_JY, b), t, pitch);
+        occ_plane(a, OC_JWX, b)[p] = jx;
+        occ_plane(a, OC_JWY, b)[p] = jy;
+        occ_plane(a, OC_RHO_C_1, b)[p] = jw - jx * u1 - jy * u2 - i0;
+    }
+}
+
+// v-update with the chi switch (:657-713) + k = theta*beta*grad(chi) (:716, used at :353-354 and :736-737)
+__global__ void __launch_bounds__(256) occ_v_kernel(OccArgs a, int it) {
+    const int b = blockIdx.z;
+    if (!occ_active(a, b, it)) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    if (x >= w || y >= h) return;
+    const int p = y * pitch + x;
+    const float u1 = occ_plane(a, OC_U1, b)[p], u2 = occ_plane(a, OC_U2, b)[p];
+    const float *chi = occ_plane(a, OC_CHI0, b);
+    const float c = chi[p];
+    const float I1wx = occ_plane(a, OC_I1WX, b)[p], I1wy = occ_plane(a, OC_I1WY, b)[p];
+    const float Jwx = occ_plane(a, OC_JWX, b)[p], Jwy = occ_plane(a, OC_JWY, b)[p];
+    const float rho_1 = occ_plane(a, OC_RHO_C1, b)[p] + I1wx * u1 + I1wy * u2;
+    const float rho__1 = occ_plane(a, OC_RHO_C_1, b)[p] + Jwx * u1 + Jwy * u2;
+    const float alpha = a.alpha, theta = a.theta, l_t = a.l_t;
+    int eps;
+    float alpha_i, mu, Lambda, grad, Iwx, Iwy, rho;
+    if (c == 0) {
+        eps = 1;
+        alpha_i = 1;
+        mu = l_t;
+        Lambda = rho_1;
+        grad = I1wx * I1wx + I1wy * I1wy;
+        Iwx = I1wx;
+        Iwy = I1wy;
+        rho = rho_1;
+    } else {
+        eps = -1;
+        alpha_i = 1 / (1 + alpha * theta);
+        mu = l_t / (1 + alpha * theta);
+        Lambda = rho__1 + alpha * theta / (1 + alpha * theta) * (u1 * Jwx + u2 * Jwy);
+        grad = Jwx * Jwx + Jwy * Jwy;
+        Iwx = Jwx;
+        Iwy = Jwy;
+        rho = rho__1;
+    }
+    float v1, v2;
+    if (Lambda > mu * grad) {
+        v1 = alpha_i * u1 - mu * eps * Iwx;
+        v2 = alpha_i * u2 - mu * eps * Iwy;
+    } else if (Lambda < -mu * grad) {
+        v1 = alpha_i * u1 + mu * eps * Iwx;
+        v2 = alpha_i * u2 + mu * eps * Iwy;
+    } else if (grad_is_zero(grad)) {
+        v1 = u1;
+        v2 = u2;
+    } else {
+        v1 = u1 - eps * rho * Iwx / grad;
+        v2 = u2 - eps * rho * Iwy / grad;
+    }
+    occ_plane(a, OC_V1, b)[p] = v1;
+    occ_plane(a, OC_V2, b)[p] = v2;
+    const float chix = (x < w - 1) ? chi[p + 1] - c : 0.f;
+    const float chiy = (y < h - 1) ? chi[p + pitch] - c : 0.f;
+    occ_plane(a, OC_K1, b)[p] = theta * a.beta * chix;
+    occ_plane(a, OC_K2, b)[p] = theta * a.beta * chiy;
+}
+
+// div(g*xi_a, g*xi_b) at pixel (x,y), recomputing the products (:343-351)
+__device__ __forceinline__ float occ_div_gxi(const float *__restrict__ g, const float *__restrict__ xa,
+                                             const float *__restrict__ xb, int x, int y, int w, int h, int pitch) {
+    const int p = y * pitch + x;
+    const float a_c = g[p] * xa[p];
+    const float b_c = g[p] * xb[p];
+    const float a_l = (x > 0) ? g[p - 1] * xa[p - 1] : 0.f;
+    const float b_u = (y > 0) ? g[p - pitch] * xb[p - pitch] : 0.f;
+    return div_bc(a_c, a_l, b_c, b_u, x, y, w, h);
+}
+
+// one Chambolle sweep for xi (:340-392), set `src` -> set `src^1`
+__global__ void __launch_bounds__(256) occ_xi_sweep_kernel(OccArgs a, int it, int src) {
+    const int b = blockIdx.z;
+    if (!occ_active(a, b, it)) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    if (x >= w || y >= h) return;
+    const int p = y * pitch + x;
+    const float *g = occ_plane(a, OC_G, b);
+    const float *xin = occ_plane(a, src ? OC_XI1 : OC_XI0, b);
+    float *xout = occ_plane(a, src ? OC_XI0 : OC_XI1, b);
+    const size_t ks = (size_t)a.g.B * a.g.plane;
+    const float theta = a.theta, tt = a.tau_theta;
+    const float gp = g[p];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {  // c = 0: (xi11, xi12, v1, k1);  c = 1: (xi21, xi22, v2, k2)
+        const float *xa = xin + (size_t)(2 * c) * ks, *xb = xin + (size_t)(2 * c + 1) * ks;
+        const float *v = occ_plane(a, OC_V1 + c, b), *k = occ_plane(a, OC_K1 + c, b);
+        // vi = v + theta*div(g xi) + theta*beta*chi_grad   (:353-354) at p, p+1, p+pitch
+        const float vi_c = v[p] + theta * occ_div_gxi(g, xa, xb, x, y, w, h, pitch) + k[p];
+        float gx = 0.f, gy = 0.f;
+        if (x < w - 1) {
+            const float vi_r = v[p + 1] + theta * occ_div_gxi(g, xa, xb, x + 1, y, w, h, pitch) + k[p + 1];
+            gx = vi_r - vi_c;
+        }
+        if (y < h - 1) {
+            const float vi_d = v[p + pitch] + theta * occ_div_gxi(g, xa, xb, x, y + 1, w, h, pitch) + k[p + pitch];
+            gy = vi_d - vi_c;
+        }
+        const float e1 = gp * gx, e2 = gp * gy;
+        const float nrm = sqrtf(e1 * e1 + e2 * e2);
+        xout[(size_t)(2 * c) * ks + p] = (xa[p] + tt * e1) / (1 + tt * nrm);
+        xout[(size_t)(2 * c + 1) * ks + p] = (xb[p] + tt * e2) / (1 + tt * nrm);
+    }
+}
+
+// final divergence, u-update, |du|^2, F and G (:394-406, :726-751)
+__global__ void __launch_bounds__(256) occ_u_kernel(OccArgs a, int it) {
+    const int b = blockIdx.z;
+    if (!occ_active(a, b, it)) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    float e = 0.f;
+    if (x < w && y < h) {
+        const int p = y * pitch + x;
+        const float *g = occ_plane(a, OC_G, b);
+        const float *xi = occ_plane(a, OC_XI0, b);  // 24 sweeps: back in set 0
+        const size_t ks = (size_t)a.g.B * a.g.plane;
+        const float theta = a.theta;
+        const float v1 = occ_plane(a, OC_V1, b)[p], v2 = occ_plane(a, OC_V2, b)[p];
+        const float dv1 = occ_div_gxi(g, xi, xi + ks, x, y, w, h, pitch);
+        const float dv2 = occ_div_gxi(g, xi + 2 * ks, xi + 3 * ks, x, y, w, h, pitch);
+        float *U1 = occ_plane(a, OC_U1, b), *U2 = occ_plane(a, OC_U2, b);
+        const float u1k = U1[p], u2k = U2[p];
+        const float u1 = v1 + theta * dv1 + occ_plane(a, OC_K1, b)[p];
+        const float u2 = v2 + theta * dv2 + occ_plane(a, OC_K2, b)[p];
+        U1[p] = u1;
+        U2[p] = u2;
+        e = (u1 - u1k) * (u1 - u1k) + (u2 - u2k) * (u2 - u2k);
+        const float rho__1 = occ_plane(a, OC_RHO_C_1, b)[p] + occ_plane(a, OC_JWX, b)[p] * v1 + occ_plane(a, OC_JWY, b)[p] * v2;
+        const float rho_1 = occ_plane(a, OC_RHO_C1, b)[p] + occ_plane(a, OC_I1WX, b)[p] * v1 + occ_plane(a, OC_I1WY, b)[p] * v2;
+        occ_plane(a, OC_F, b)[p] = a.lambda * (fabsf(rho__1) - fabsf(rho_1));
+        occ_plane(a, OC_GG, b)[p] = a.alpha / 2 * (v1 * v1 + v2 * v2);
+    }
+    __shared__ float red[8];
+    e = warp_max(e);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) red[tid >> 5] = e;
+    __syncthreads();
+    if (tid == 0) {
+        float m = red[0];
+        for (int i = 1; i < (int)(blockDim.x * blockDim.y / 32); i++) m = fmaxf(m, red[i]);
+        atomicMax(a.err_max + (size_t)b * a.max_iters + it, __float_as_uint(m));
+    }
+}
+
+// eta_new at pixel (x,y) from the old eta and the current chi (:439-452)
+__device__ __forceinline__ void occ_eta_new(const float *__restrict__ eta1, const float *__restrict__ eta2,
+                                            const float *__restrict__ chi, const float *__restrict__ g, float mte, int x,
+                                            int y, int w, int h, int pitch, float &o1, float &o2) {
+    const int p = y * pitch + x;
+    const float c = chi[p];
+    const float chix = (x < w - 1) ? chi[p + 1] - c : 0.f;
+    const float chiy = (y < h - 1) ? chi[p + pitch] - c : 0.f;
+    const float e1 = eta1[p] + mte * g[p] * chix;
+    const float e2 = eta2[p] + mte * g[p] * chiy;
+    const float ne = sqrtf(e1 * e1 + e2 * e2);
+    if (ne <= 1) {
+        o1 = e1;
+        o2 = e2;
+    } else {
+        o1 = e1 / ne;
+        o2 = e2 / ne;
+    }
+}
+
+// one primal-dual sweep for chi (:431-474); the last one also thresholds (:476-483)
+__global__ void __launch_bounds__(256) occ_chi_sweep_kernel(OccArgs a, int it, int src, int last) {
+    const int b = blockIdx.z;
+    if (!occ_active(a, b, it)) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    if (x >= w || y >= h) return;
+    const int p = y * pitch + x;
+    const float *g = occ_plane(a, OC_G, b);
+    const float *e1 = occ_plane(a, src ? OC_ETA1 : OC_ETA0, b), *e2 = e1 + (size_t)a.g.B * a.g.plane;
+    float *o1 = occ_plane(a, src ? OC_ETA0 : OC_ETA1, b), *o2 = o1 + (size_t)a.g.B * a.g.plane;
+    const float *chi = occ_plane(a, src ? OC_CHI1 : OC_CHI0, b);
+    float *chio = occ_plane(a, src ? OC_CHI0 : OC_CHI1, b);
+    const float mte = a.mu * a.tau_eta;
+    float n1, n2, l1 = 0.f, l2 = 0.f, t1 = 0.f, t2 = 0.f;
+    occ_eta_new(e1, e2, chi, g, mte, x, y, w, h, pitch, n1, n2);
+    if (x > 0) occ_eta_new(e1, e2, chi, g, mte, x - 1, y, w, h, pitch, l1, l2);
+    if (y > 0) occ_eta_new(e1, e2, chi, g, mte, x, y - 1, w, h, pitch, t1, t2);
+    o1[p] = n1;
+    o2[p] = n2;
+    const float a_c = g[p] * n1, b_c = g[p] * n2;
+    const float a_l = (x > 0) ? g[p - 1] * l1 : 0.f;
+    const float b_u = (y > 0) ? g[p - pitch] * t2 : 0.f;
+    const float dge = div_bc(a_c, a_l, b_c, b_u, x, y, w, h);
+    const float div_u = 0.f;  // target definition
+    const float cn = chi[p] + a.tau_chi * (a.mu * dge - a.beta * div_u - occ_plane(a, OC_F, b)[p] - occ_plane(a, OC_GG, b)[p]);
+    const float lo = (cn < 1) ? cn : 1;
+    float c = (lo > 0) ? lo : 0;
+    if (last) c = ((double)c > 0.6) ? 1.f : 0.f;
+    chio[p] = c;
+}
+
+__global__ void occ_export_kernel(OccArgs a, float *packed) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= a.g.w || y >= a.g.h) return;
+    const size_t n = (size_t)a.g.w * a.g.h;
+    const int p = y * a.g.pitch + x;
+    float *o = packed + (size_t)b * 3 * n + (size_t)y * a.g.w + x;
+    o[0] = occ_plane(a, OC_U1, b)[p];
+    o[n] = occ_plane(a, OC_U2, b)[p];
+    o[2 * n] = occ_plane(a, OC_CHI0, b)[p];
+}
+
+}  // namespace faldoi

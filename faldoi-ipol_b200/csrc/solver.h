@@ -1,0 +1,63 @@
+// Host-side state of one batched solver handle (C++ side of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/faldoi_gpu.h"
+#include "common.cuh"
+
+namespace faldoi {
+
+void set_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what);
+
+#define FALDOI_CUDA(call)                                   \
+    do {                                                    \
+        if (!::faldoi::cuda_ok((call), #call)) return FALDOI_ERR_CUDA; \
+    } while (0)
+
+enum Family { FAM_TV = 0, FAM_NLTV = 1, FAM_OCC = 2 };
+
+inline bool method_is_csad(int m) { return m == 4 || m == 5 || m == 6 || m == 7; }
+inline bool method_is_nltv(int m) { return m == 2 || m == 3 || m == 6 || m == 7; }
+inline Family method_family(int m) { return m == 8 ? FAM_OCC : (method_is_nltv(m) ? FAM_NLTV : FAM_TV); }
+
+}  // namespace faldoi
+
+struct faldoi_solver {
+    int device = 0, method = 0, B = 0;
+    faldoi::Geo g{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> allocs;  // everything cudaMalloc'ed, freed in destroy
+
+    // static per-pair planes
+    float *I0 = nullptr, *I1 = nullptr, *I1x = nullptr, *I1y = nullptr;
+    // TV / NLTV state (2 ping-pong sets) and per-warp constants
+    float *state = nullptr;
+    size_t set_stride = 0;
+    float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr, *bs = nullptr;
+    // NLTV: Lab, weights, duals
+    float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *dual = nullptr;
+    size_t dual_set_stride = 0;
+    // OCC planes
+    float *occ = nullptr;  // see occ_kernels.cuh for the layout
+    // control
+    unsigned *err_max = nullptr;
+    double *err_sum = nullptr;
+    int *parity = nullptr;
+    int *log_iters = nullptr;
+    float *log_err = nullptr;
+    int err_cap = 0;  // max_iters capacity of err arrays
+    // packed export buffer [B][3][h][w] (u1,u2,chi) for plain D2H copies
+    float *packed = nullptr;
+
+    float last_ms = 0.f;
+    long long launches = 0;
+    bool ran = false;
+
+    float *dmalloc(size_t nfloats);
+    int alloc_err(int max_iters);
+};

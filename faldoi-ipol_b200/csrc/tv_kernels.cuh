@@ -1,0 +1,401 @@
+// Fused primal-dual iteration for the TV-regularised models:
+//   DATA_TVL1 : tvl2OF     (methods 0,1)  src/global_faldoi.cpp:684-784
+//   DATA_CSAD : tvcsad_PD  (methods 4,5)  src/global_faldoi.cpp:1543-1620
+//
+// One launch = one iteration over all active pairs of the batch.  The
+// reference's 7 passes per iteration (TH, 2x forward_gradient, getD,
+// 2x divergence, memcpy, getP, extrapolation; 52 words/px) become one pass
+// that reads 11 planes and writes 8 (76 B/px): u, ubar, xi x4, and the
+// per-warp constants.
+//
+// Thread mapping: a thread owns 4 consecutive pixels (one float4) of R
+// consecutive rows and marches down them; a warp covers 128 columns.  The
+// stencil dependencies are resolved in registers:
+//   * xi_new(p-1)   (backward x-difference of div): warp shuffle from the
+//                    left lane; lane 0 recomputes it from 7 scalar loads,
+//   * xi_new(p-w)   (backward y-difference): carried from the previous row of
+//                    the march; recomputed once for the row above the strip,
+//   * ubar(p+1)      shuffle from the right lane (lane 31: one scalar load),
+//   * ubar(p+w)      the next row's float4, reused as the current row next step.
+// All state planes are double-buffered (set `par` -> set `par^1`) because
+// neighbouring threads need the OLD ubar / xi of pixels another CTA rewrites.
+#pragma once
+#include "common.cuh"
+
+namespace faldoi {
+
+enum { DATA_TVL1 = 0, DATA_CSAD = 1 };
+enum { ST_U1 = 0, ST_U2, ST_UB1, ST_UB2, ST_XI11, ST_XI12, ST_XI21, ST_XI22, ST_COUNT };
+
+struct TvArgs {
+    float *state;        // [2 sets][ST_COUNT][B] planes
+    size_t set_stride;   // floats between set 0 and set 1
+    const float *Ix, *Iy;  // [B] warped gradient of I1
+    const float *rho_c;    // [B] TVL1 data term constant
+    const float *scale;    // [B] CSAD: hypot(Ix^2+Iy^2, 0.01)
+    const float *bs;       // [48][B] CSAD: neighbour residuals b_j sorted descending per pixel
+    unsigned *err_max;     // [B][max_iters] float bits of max |du|^2     (DATA_TVL1)
+    double *err_sum;       // [B][max_iters] sum of |du|^2                  (DATA_CSAD)
+    const int *parity;     // [B]
+    Geo g;
+    int max_iters;
+    float tau, theta, l_t, tol2;
+};
+
+// Has pair b already met the reference's exit test `err > tol^2` (false = stop)
+// after iteration it-1?  Entries of iterations that never ran stay 0 -> stop.
+template <int DATA>
+__device__ __forceinline__ bool pair_active(const TvArgs &a, int b, int it) {
+    if (it == 0) return true;
+    float e;
+    if (DATA == DATA_TVL1)
+        e = __uint_as_float(a.err_max[(size_t)b * a.max_iters + it - 1]);
+    else
+        e = (float)a.err_sum[(size_t)b * a.max_iters + it - 1] / (float)(a.g.w * a.g.h);
+    return e > a.tol2;
+}
+
+// rank selection of the CSAD data term (src/global_faldoi.cpp:1549-1570): the
+// element of index n+1 of sort({-(b_j - s)} U {(n-2k)*l_t*scale, k=0..n}).
+// With a_m = -(bs_m - s) ascending (bs sorted descending) and the thresholds
+// t_m descending, that element equals min_m max(a_m, t_m), m = 0..n-1, found
+// by bisection on the monotone predicate a_m >= t_m  ("CSAD rank").
+__device__ __forceinline__ float csad_select(const float *__restrict__ bs, size_t stride, int np, float s,
+                                             float l_t, float scale) {
+    int lo = 0, hi = np;
+    float a_lo = 0.f;  // a(lo) when lo < np is the final answer candidate
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float am = -(__ldg(bs + (size_t)mid * stride) - s);
+        const float tm = (float)(np - 2 * mid) * l_t * scale;
+        if (am >= tm) {
+            hi = mid;
+            a_lo = am;
+        } else {
+            lo = mid + 1;
+        }
+    }
+    float ans = INFINITY;
+    if (lo < np) ans = a_lo;  // a(lo): lo == last hi for which the predicate held
+    if (lo > 0) ans = fminf(ans, (float)(np - 2 * (lo - 1)) * l_t * scale);
+    return ans;
+}
+
+__device__ __forceinline__ int csad_count(int x, int y, int w, int h) {
+    const int nx = min(x, 3) + min(w - 1 - x, 3) + 1;
+    const int ny = min(y, 3) + min(h - 1 - y, 3) + 1;
+    return nx * ny - 1;
+}
+
+template <int R, int DATA>
+__global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
+    const int b = blockIdx.z;
+    if (!pair_active<DATA>(a, b, it)) return;
+
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    const int lane = threadIdx.x;
+    const int x = (blockIdx.x * 32 + lane) * 4;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * R;
+    const bool xin = x < pitch;
+
+    const int par = (a.parity[b] + it) & 1;
+    const size_t B = a.g.B, plane = a.g.plane;
+    const float *in = a.state + (size_t)par * a.set_stride + (size_t)b * plane;
+    float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
+    const size_t ks = B * plane;  // stride between state kinds
+    const float *cIx = a.Ix + (size_t)b * plane, *cIy = a.Iy + (size_t)b * plane;
+    const float tau = a.tau, theta = a.theta, l_t = a.l_t;
+
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto LD = [&](const float *base, int row) -> float4 {
+        return xin ? ld4(base + (size_t)row * pitch + x) : z4;
+    };
+
+    // ubar of the current row (+ right neighbour), carried down the march
+    float b1[5], b2[5];
+    {
+        const int yc = min(y0, h - 1);  // warps below the image only take part in the reduction
+        const float4 t1 = LD(in + ST_UB1 * ks, yc), t2 = LD(in + ST_UB2 * ks, yc);
+        b1[0] = t1.x, b1[1] = t1.y, b1[2] = t1.z, b1[3] = t1.w;
+        b2[0] = t2.x, b2[1] = t2.y, b2[2] = t2.z, b2[3] = t2.w;
+    }
+
+    // xi_new12 / xi_new22 of the row above the strip
+    float p12[4] = {0.f, 0.f, 0.f, 0.f}, p22[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y0 > 0 && y0 < h) {
+        const int yu = y0 - 1;
+        const float4 q11 = LD(in + ST_XI11 * ks, yu), q12 = LD(in + ST_XI12 * ks, yu);
+        const float4 q21 = LD(in + ST_XI21 * ks, yu), q22 = LD(in + ST_XI22 * ks, yu);
+        const float4 c1 = LD(in + ST_UB1 * ks, yu), c2 = LD(in + ST_UB2 * ks, yu);
+        const float x11[4] = {q11.x, q11.y, q11.z, q11.w}, x12[4] = {q12.x, q12.y, q12.z, q12.w};
+        const float x21[4] = {q21.x, q21.y, q21.z, q21.w}, x22[4] = {q22.x, q22.y, q22.z, q22.w};
+        const float u1a[4] = {c1.x, c1.y, c1.z, c1.w}, u2a[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float u1y = b1[k] - u1a[k], u2y = b2[k] - u2a[k];  // yu < h-1 always
+            if (DATA == DATA_TVL1) {
+                const float nrm = fmaxf(1.f, sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]));
+                p12[k] = (x12[k] + tau * u1y) / nrm;
+                p22[k] = (x22[k] + tau * u2y) / nrm;
+            } else {
+                const float n1 = fmaxf(1.f, hypotf_exact(x11[k], x12[k]));
+                const float n2 = fmaxf(1.f, hypotf_exact(x21[k], x22[k]));
+                p12[k] = (x12[k] + tau * u1y) / n1;
+                p22[k] = (x22[k] + tau * u2y) / n2;
+            }
+        }
+    }
+
+    float emax = 0.f;
+    double esum = 0.0;
+
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int y = y0 + r;
+        if (y >= h) break;  // warp-uniform (a warp shares y0)
+        const bool ylast = (y == h - 1);
+        // ---- loads of this row ----
+        const float4 q11 = LD(in + ST_XI11 * ks, y), q12 = LD(in + ST_XI12 * ks, y);
+        const float4 q21 = LD(in + ST_XI21 * ks, y), q22 = LD(in + ST_XI22 * ks, y);
+        const float4 qu1 = LD(in + ST_U1 * ks, y), qu2 = LD(in + ST_U2 * ks, y);
+        const float4 qix = LD(cIx, y), qiy = LD(cIy, y);
+        float4 qn1 = z4, qn2 = z4;
+        if (!ylast) {
+            qn1 = LD(in + ST_UB1 * ks, y + 1);
+            qn2 = LD(in + ST_UB2 * ks, y + 1);
+        }
+        float4 qrc = z4, qsc = z4;
+        if (DATA == DATA_TVL1)
+            qrc = LD(a.rho_c + (size_t)b * plane, y);
+        else
+            qsc = LD(a.scale + (size_t)b * plane, y);
+
+        // right neighbour of ubar: from the next lane, lane 31 loads it
+        b1[4] = __shfl_down_sync(0xffffffffu, b1[0], 1);
+        b2[4] = __shfl_down_sync(0xffffffffu, b2[0], 1);
+        if (lane == 31 && x + 4 < w) {
+            b1[4] = in[ST_UB1 * ks + (size_t)y * pitch + x + 4];
+            b2[4] = in[ST_UB2 * ks + (size_t)y * pitch + x + 4];
+        }
+
+        const float x11[4] = {q11.x, q11.y, q11.z, q11.w}, x12[4] = {q12.x, q12.y, q12.z, q12.w};
+        const float x21[4] = {q21.x, q21.y, q21.z, q21.w}, x22[4] = {q22.x, q22.y, q22.z, q22.w};
+        const float n1r[4] = {qn1.x, qn1.y, qn1.z, qn1.w}, n2r[4] = {qn2.x, qn2.y, qn2.z, qn2.w};
+        const float u1[4] = {qu1.x, qu1.y, qu1.z, qu1.w}, u2[4] = {qu2.x, qu2.y, qu2.z, qu2.w};
+        const float ix[4] = {qix.x, qix.y, qix.z, qix.w}, iy[4] = {qiy.x, qiy.y, qiy.z, qiy.w};
+        const float rc[4] = {qrc.x, qrc.y, qrc.z, qrc.w}, sc[4] = {qsc.x, qsc.y, qsc.z, qsc.w};
+
+        // ---- dual step: xi <- (xi + tau*grad(ubar)) / max(1, |xi_old|) ----
+        float m11[4], m12[4], m21[4], m22[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = x + k;
+            const float u1x = (gx < w - 1) ? b1[k + 1] - b1[k] : 0.f;
+            const float u2x = (gx < w - 1) ? b2[k + 1] - b2[k] : 0.f;
+            const float u1y = ylast ? 0.f : n1r[k] - b1[k];
+            const float u2y = ylast ? 0.f : n2r[k] - b2[k];
+            if (DATA == DATA_TVL1) {
+                const float nrm = fmaxf(1.f, sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]));
+                m11[k] = (x11[k] + tau * u1x) / nrm;
+                m12[k] = (x12[k] + tau * u1y) / nrm;
+                m21[k] = (x21[k] + tau * u2x) / nrm;
+                m22[k] = (x22[k] + tau * u2y) / nrm;
+            } else {
+                const float n1 = fmaxf(1.f, hypotf_exact(x11[k], x12[k]));
+                const float n2 = fmaxf(1.f, hypotf_exact(x21[k], x22[k]));
+                m11[k] = (x11[k] + tau * u1x) / n1;
+                m12[k] = (x12[k] + tau * u1y) / n1;
+                m21[k] = (x21[k] + tau * u2x) / n2;
+                m22[k] = (x22[k] + tau * u2y) / n2;
+            }
+        }
+
+        // xi_new11 / xi_new21 of the pixel to the left of this thread's quad
+        float l11 = __shfl_up_sync(0xffffffffu, m11[3], 1);
+        float l21 = __shfl_up_sync(0xffffffffu, m21[3], 1);
+        if (lane == 0 && x > 0) {
+            const size_t o = (size_t)y * pitch + x - 1;
+            const float e11 = in[ST_XI11 * ks + o], e12 = in[ST_XI12 * ks + o];
+            const float e21 = in[ST_XI21 * ks + o], e22 = in[ST_XI22 * ks + o];
+            const float c1 = in[ST_UB1 * ks + o], c2 = in[ST_UB2 * ks + o];
+            const float u1x = b1[0] - c1, u2x = b2[0] - c2;  // x-1 < w-1 always
+            if (DATA == DATA_TVL1) {
+                const float nrm = fmaxf(1.f, sqrtf(e11 * e11 + e12 * e12 + e21 * e21 + e22 * e22));
+                l11 = (e11 + tau * u1x) / nrm;
+                l21 = (e21 + tau * u2x) / nrm;
+            } else {
+                l11 = (e11 + tau * u1x) / fmaxf(1.f, hypotf_exact(e11, e12));
+                l21 = (e21 + tau * u2x) / fmaxf(1.f, hypotf_exact(e21, e22));
+            }
+        }
+
+        // ---- data term, primal step, extrapolation ----
+        float o1[4], o2[4], ob1[4], ob2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = x + k;
+            const float d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, y, w, h);
+            const float d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, y, w, h);
+            float v1, v2;
+            if (DATA == DATA_TVL1) {
+                // thresholding operator TH (src/global_faldoi.cpp:693-717)
+                const float grad = ix[k] * ix[k] + iy[k] * iy[k];
+                const float rho = rc[k] + (ix[k] * u1[k] + iy[k] * u2[k]);
+                float e1, e2;
+                if (rho < -l_t * grad) {
+                    e1 = l_t * ix[k];
+                    e2 = l_t * iy[k];
+                } else if (rho > l_t * grad) {
+                    e1 = -l_t * ix[k];
+                    e2 = -l_t * iy[k];
+                } else if (grad_is_zero(grad)) {
+                    e1 = e2 = 0.f;
+                } else {
+                    const float fi = -rho / grad;
+                    e1 = fi * ix[k];
+                    e2 = fi * iy[k];
+                }
+                v1 = u1[k] + e1;
+                v2 = u2[k] + e2;
+            } else {
+                v1 = u1[k];
+                v2 = u2[k];
+                if (gx < w) {
+                    const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / sc[k];
+                    const int np = csad_count(gx, y, w, h);
+                    const float med = csad_select(a.bs + (size_t)b * plane + (size_t)y * pitch + gx, ks, np, s, l_t, sc[k]);
+                    v1 = u1[k] - ix[k] * med / sc[k];
+                    v2 = u2[k] - iy[k] * med / sc[k];
+                }
+            }
+            // primal step (ofTVl2_getP :325-335) and extrapolation (:780-783)
+            o1[k] = u1[k] - tau * (-d1 + (u1[k] - v1) / theta);
+            o2[k] = u2[k] - tau * (-d2 + (u2[k] - v2) / theta);
+            const float e = (o1[k] - u1[k]) * (o1[k] - u1[k]) + (o2[k] - u2[k]) * (o2[k] - u2[k]);
+            if (gx < w) {
+                emax = fmaxf(emax, e);
+                if (DATA == DATA_CSAD) esum += (double)e;
+            }
+            ob1[k] = 2 * o1[k] - u1[k];
+            ob2[k] = 2 * o2[k] - u2[k];
+        }
+
+        if (xin) {
+            const size_t o = (size_t)y * pitch + x;
+            st4(out + ST_XI11 * ks + o, make_float4(m11[0], m11[1], m11[2], m11[3]));
+            st4(out + ST_XI12 * ks + o, make_float4(m12[0], m12[1], m12[2], m12[3]));
+            st4(out + ST_XI21 * ks + o, make_float4(m21[0], m21[1], m21[2], m21[3]));
+            st4(out + ST_XI22 * ks + o, make_float4(m22[0], m22[1], m22[2], m22[3]));
+            st4(out + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+            st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+            st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+        }
+        // carry to the next row of the march
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            p12[k] = m12[k];
+            p22[k] = m22[k];
+            b1[k] = n1r[k];
+            b2[k] = n2r[k];
+        }
+    }
+
+    // ---- convergence measure: warp shuffle -> shared -> one atomic per CTA ----
+    __shared__ float red_max[8];
+    __shared__ double red_sum[8];
+    if (DATA == DATA_TVL1) {
+        emax = warp_max(emax);
+        if (lane == 0) red_max[threadIdx.y] = emax;
+    } else {
+        esum = warp_sum(esum);
+        if (lane == 0) red_sum[threadIdx.y] = esum;
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && lane == 0) {
+        if (DATA == DATA_TVL1) {
+            float m = red_max[0];
+            for (int i = 1; i < (int)blockDim.y; i++) m = fmaxf(m, red_max[i]);
+            atomicMax(a.err_max + (size_t)b * a.max_iters + it, __float_as_uint(m));
+        } else {
+            double t = red_sum[0];
+            for (int i = 1; i < (int)blockDim.y; i++) t += red_sum[i];
+            atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CSAD per-warp constants (src/global_faldoi.cpp:1514-1534): scale =
+// hypot(Ix^2+Iy^2, 0.01) and, for the in-image neighbours j of the 7x7 window,
+//   b_j = (I0[p] - I0[j] - I1w[p] + I1w[j] + Ix*u1 + Iy*u2) / scale
+// stored SORTED DESCENDING per pixel (48 planes) so the per-iteration rank
+// selection is a bisection instead of the reference's std::sort of 97 floats.
+// hyp = 0 is the NLTV-CSAD variant (:1698-1723): scale = sqrt(Ix^2+Iy^2),
+// only where Ix^2+Iy^2 > 1e-8 (elsewhere scale := 0 marks "v = u").
+// ---------------------------------------------------------------------------
+struct CsadArgs {
+    const float *I0, *I1w, *Ix, *Iy;  // [B]
+    const float *u1, *u2;             // flow planes base (+parity*set_stride)
+    const int *parity;
+    size_t set_stride;
+    float *scale;  // [B]
+    float *bs;     // [48][B]
+    Geo g;
+    int hyp;
+};
+
+__global__ void __launch_bounds__(128) csad_constants_kernel(CsadArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    if (x >= w || y >= h) return;
+    const size_t off = (size_t)b * a.g.plane;
+    const size_t so = off + (size_t)a.parity[b] * a.set_stride;
+    const int p = y * pitch + x;
+    const float ix = a.Ix[off + p], iy = a.Iy[off + p];
+    const float g2 = ix * ix + iy * iy;
+    float scale;
+    if (a.hyp) {
+        scale = (float)hypot((double)g2, 0.01);
+    } else {
+        if (!grad_above_zero(g2)) {
+            a.scale[off + p] = 0.f;
+            return;
+        }
+        scale = sqrtf(g2);
+    }
+    a.scale[off + p] = scale;
+    const float u1 = a.u1[so + p], u2 = a.u2[so + p];
+    const float *I0 = a.I0 + off, *I1w = a.I1w + off;
+    const float i0p = I0[p], iwp = I1w[p];
+    const float t1 = ix * u1, t2 = iy * u2;
+
+    float bv[48];
+    int s = 0;
+#pragma unroll
+    for (int k = -3; k <= 3; k++)
+#pragma unroll
+        for (int l = -3; l <= 3; l++) {
+            if (k == 0 && l == 0) continue;
+            const int r = y + k, c = x + l;
+            float v = -INFINITY;  // out-of-image slots sort to the end
+            if (c >= 0 && c < w && r >= 0 && r < h) {
+                const int q = r * pitch + c;
+                v = (i0p - __ldg(I0 + q) - iwp + __ldg(I1w + q) + t1 + t2) / scale;
+            }
+            bv[s++] = v;
+        }
+    // rank sort (descending, ties by slot) -- 48x48 compares, all in registers
+    const size_t ks = (size_t)a.g.B * a.g.plane;
+#pragma unroll
+    for (int i = 0; i < 48; i++) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 48; j++) rank += (bv[j] > bv[i]) || (bv[j] == bv[i] && j < i);
+        a.bs[(size_t)rank * ks + off + p] = bv[i];
+    }
+}
+
+}  // namespace faldoi

@@ -1,0 +1,150 @@
+/* faldoi_gpu.h -- C ABI of libfaldoi_gpu.so, the B200 (sm_100a) implementation of
+ * FALDOI's global variational minimisation (the `global_faldoi` pass).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the reference repository).  All images are planar row-major fp32 (x[j*w+i]),
+ * already gray / normalised / smoothed exactly as the reference's main() does
+ * (src/global_faldoi.cpp:2049-2068) unless the function says otherwise.
+ *
+ * There is NO CPU fallback: every call returns FALDOI_ERR_CUDA (and
+ * faldoi_last_error() says why) when no sm_100 device / driver is usable.
+ */
+#ifndef FALDOI_GPU_H
+#define FALDOI_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* energy-model ids: src/parameters.h:5-13 */
+enum {
+    FALDOI_M_TVL1 = 0,
+    FALDOI_M_TVL1_W = 1,
+    FALDOI_M_NLTVL1 = 2,
+    FALDOI_M_NLTVL1_W = 3,
+    FALDOI_M_TVCSAD = 4,
+    FALDOI_M_TVCSAD_W = 5,
+    FALDOI_M_NLTVCSAD = 6,
+    FALDOI_M_NLTVCSAD_W = 7,
+    FALDOI_M_TVL1_OCC = 8
+};
+
+enum {
+    FALDOI_OK = 0,
+    FALDOI_ERR_ARG = 1,  /* bad argument (null pointer, size, unknown method) */
+    FALDOI_ERR_CUDA = 2, /* CUDA runtime / no usable device */
+    FALDOI_ERR_MEM = 3   /* allocation failed */
+};
+
+#define FALDOI_MAX_WARPS 64
+
+/* Scalars of `Parameters` that the global step reads (src/energy_structures.h:60-86). */
+typedef struct faldoi_params {
+    int method;    /* val_method */
+    int warps;     /* -w, default PAR_DEFAULT_NWARPS_GLOBAL = 5 (src/parameters.h:51) */
+    int max_iters; /* 400 (MAX_ITERATIONS_GLOBAL) for methods 0-7; -glb_iters for method 8 */
+    float lambda, theta, tau, beta, alpha, tau_u, tau_eta, tau_chi, mu, tol;
+} faldoi_params;
+
+/* What `-verbose 1` prints per warp ("Warping: k,Iter: n Error: e"). */
+typedef struct faldoi_log {
+    int iters[FALDOI_MAX_WARPS];
+    float err[FALDOI_MAX_WARPS];
+} faldoi_log;
+
+typedef struct faldoi_solver faldoi_solver; /* opaque; bound to one device, one frame size, one method family */
+
+/* Defaults of init_params("", GLOBAL_STEP) (src/utils_preprocess.cpp:37-63, src/parameters.h:16-55)
+ * followed by main()'s per-method overrides of lambda/theta/tau for methods 2-7
+ * (src/global_faldoi.cpp:2138-2156).  glb_iters only matters for method 8. */
+int faldoi_default_params(int method, int glb_iters, faldoi_params *out);
+
+/* Same, after reading the reference's 9-line `-p` parameter file
+ * (src/utils_preprocess.cpp:65-155: value <= 0 -> default, tau's > 0.25 -> default). */
+int faldoi_params_from_file(const char *path, int method, int glb_iters, faldoi_params *out);
+
+const char *faldoi_last_error(void);
+int faldoi_device_count(void);
+
+/* ---- batched solver handle -------------------------------------------------
+ * One handle owns the HBM state for `batch` independent frame pairs of size
+ * w x h on CUDA device `device`, plus its own stream.  Re-entrant per handle,
+ * so one host thread per GPU can drive 8 GPUs.  Replaces the work-buffer
+ * allocation inside each reference solver (src/global_faldoi.cpp:581-609,
+ * 1195-1211, 1472-1503, 1660-1678; src/tvl2_model_occ.cpp:30-104). */
+int faldoi_solver_create(faldoi_solver **out, int device, int w, int h, int method, int batch);
+void faldoi_solver_destroy(faldoi_solver *s);
+
+/* Upload pair `slot` (0 <= slot < batch) from host memory.
+ *   I0,I1   preprocessed gray frames (w*h)
+ *   Im1     preprocessed previous frame (w*h), method 8 only, else may be NULL
+ *   lab     Lab image of I0 from image_to_lab (3*w*h planar), NLTV methods only, else NULL
+ *   u       initial flow, 2*w*h planar (u1 | u2), e.g. the local_faldoi output
+ *   chi     initial occlusion mask (w*h), method 8 only, else NULL
+ * Dual variables are reset to 0 as main() does (src/global_faldoi.cpp:2116-2121). */
+int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0, const float *I1, const float *Im1,
+                         const float *lab, const float *u, const float *chi);
+
+/* Run the primal-dual minimisation on slots [0, npairs) with everything resident in HBM.
+ * Replaces the bodies of tvl2OF / nltvl1_PD / tvcsad_PD / nltvcsad_PD /
+ * guided_tvl2coupled_occ (dispatch: src/global_faldoi.cpp:2132-2167).
+ * Asynchronous on the handle's stream; faldoi_solver_sync() waits. */
+int faldoi_solver_run(faldoi_solver *s, const faldoi_params *p, int npairs);
+int faldoi_solver_sync(faldoi_solver *s);
+
+/* Download the result of pair `slot`: flow (2*w*h), and for method 8 the
+ * occlusion mask chi in {0,1} (w*h); log may be NULL. */
+int faldoi_solver_download(faldoi_solver *s, int slot, float *u, float *chi, faldoi_log *log);
+
+/* Milliseconds the last faldoi_solver_run spent on the device (CUDA events on the handle's stream). */
+float faldoi_solver_last_run_ms(faldoi_solver *s);
+/* Number of kernel launches issued by the last faldoi_solver_run. */
+long long faldoi_solver_last_launches(faldoi_solver *s);
+/* The handle's cudaStream_t (as void*) so callers can order their own work / events. */
+void *faldoi_solver_stream(faldoi_solver *s);
+/* Device pointer to the flow of pair `slot` (2 planes of h rows with the given pitch in floats). */
+float *faldoi_solver_device_flow(faldoi_solver *s, int slot, int *pitch_floats);
+
+/* ---- one-call host entry: H2D, solve, D2H ----------------------------------
+ * The single call the host `global_faldoi` makes after preprocessing
+ * (replaces src/global_faldoi.cpp:2132-2167).  u (and chi) are updated in place. */
+int faldoi_global_solve(int device, const faldoi_params *p, int w, int h, const float *I0, const float *I1,
+                        const float *Im1, const float *lab, float *u, float *chi, faldoi_log *log);
+
+/* ---- per-solver mirrors of the reference's in-process signatures -----------
+ * Same argument order and in-place semantics as the reference functions; the
+ * only addition is the int status.  `verbose` prints the reference's per-warp
+ * line to stderr (methods 0,4) / stdout (methods 2,6).
+ *   tvl2OF       src/global_faldoi.cpp:556-573
+ *   tvcsad_PD    src/global_faldoi.cpp:1449-1466
+ *   nltvl1_PD    src/global_faldoi.cpp:1177-1191
+ *   nltvcsad_PD  src/global_faldoi.cpp:1642-1656 */
+int faldoi_tvl2OF(const float *I0, float *I1, float *u1, float *u2, float *xi11, float *xi12, float *xi21,
+                  float *xi22, float lambda, float theta, float tau, float tol_OF, int nx, int ny, int warps,
+                  int verbose);
+int faldoi_tvcsad_PD(const float *I0, float *I1, float *xi11, float *xi12, float *xi21, float *xi22,
+                     float lambda, float theta, float tau, float tol_OF, int nx, int ny, int warps, int verbose,
+                     float *u1, float *u2);
+int faldoi_nltvl1_PD(const float *I0, float *I1, float *a, int pd, float lambda, float theta, float tau, int w,
+                     int h, int warps, int verbose, float *u1, float *u2);
+int faldoi_nltvcsad_PD(const float *I0, float *I1, float *a, int pd, float lambda, float theta, float tau, int w,
+                       int h, int warps, int verbose, float *u1, float *u2);
+/* guided_tvl2coupled_occ (src/tvl2_model_occ.cpp:492-502) with the patch set to
+ * the whole image and step_algorithm = GLOBAL_STEP, scalars taken from `p`
+ * instead of ofD->params.  eta and div_u start at 0 (the reference leaves them
+ * uninitialised). */
+int faldoi_guided_tvl2coupled_occ(const float *I0, const float *I1, const float *I_1, float *u1, float *u2,
+                                  float *chi, const faldoi_params *p, int nx, int ny, int verbose);
+
+/* ---- device-side preprocessing helpers (row "next" of the scope table) ---- */
+/* centered_gradient (src/utils.cpp:367-423) and bicubic_interpolation_warp
+ * (src/bicubic_interpolation.c:245-266) on host arrays, computed on the GPU. */
+int faldoi_centered_gradient(int device, const float *in, float *dx, float *dy, int nx, int ny);
+int faldoi_bicubic_warp(int device, const float *in, const float *u, const float *v, float *out, int nx, int ny,
+                        int border_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FALDOI_GPU_H */

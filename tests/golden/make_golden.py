@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref,
+built by `make -C oracle ref` from /root/reference/src) on crops of the
+reference's own example data, with the reference's local_faldoi output as the
+initial flow (oracle/make_init_flow.sh).  Only runs where /root/reference exists;
+the committed .npz files are what travels.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pyoracle as po  # noqa: E402
+
+REF = os.environ.get("REF", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def ref_preprocess(i0, i1, im1):
+    """main()'s preprocessing through the reference's own functions."""
+    import ctypes as C
+    L = po.ref()
+    _, h, w = i0.shape
+    g = [np.empty((h, w), np.float32) for _ in range(3)]
+    for a, o in zip((i0, i1, im1), g):
+        L.ref_rgb2gray(po._p(a.copy()), w, h, po._p(o))
+    L.ref_image_normalization_3(po._p(g[0]), po._p(g[1]), po._p(g[2]), po._p(g[0]), po._p(g[1]), po._p(g[2]), w * h)
+    for o in g:
+        L.ref_gaussian(po._p(o), w, h, C.c_float(0.9))
+    lab = np.empty_like(i0)
+    L.ref_image_to_lab(po._p(i0.copy()), w * h, po._p(lab))
+    return g[0], g[1], g[2], lab
+
+
+def make_case(name, seq, x0, y0, w, h, runs):
+    E = os.path.join(REF, "example_data", seq)
+    fr = [po.read_image_planar(os.path.join(E, "frame_%04d.png" % k)) for k in (1, 2, 3)]
+    rg = po.read_flo(os.path.join(ROOT, "oracle", "_ref", "data", seq.replace("/", "_"), "rg.flo"))
+    crop = lambda a: np.ascontiguousarray(a[:, y0:y0 + h, x0:x0 + w])
+    im1, i0, i1 = [crop(f) for f in fr]
+    u0 = crop(rg)
+    I0, I1, Im1, lab = ref_preprocess(i0, i1, im1)
+    chi0 = np.zeros((h, w), np.float32)
+    chi0[h // 4:h // 2, w // 3:2 * w // 3] = 1
+    out = dict(rgb_im1=im1.astype(np.uint8), rgb_i0=i0.astype(np.uint8), rgb_i1=i1.astype(np.uint8), u0=u0, chi0=chi0,
+               I0n=I0, I1n=I1, Im1n=Im1, lab=lab, crop=np.array([x0, y0, w, h]), seq=np.array(seq))
+    for method, warps, iters in runs:
+        u, chi = po.r_global_solve(method, I0, I1, Im1, lab, u0, chi0 if method == 8 else None, warps=warps,
+                                   glb_iters=iters)
+        key = "m%d_w%d" % (method, warps) + ("_i%d" % iters if method == 8 else "")
+        out["u_" + key] = u
+        if chi is not None:
+            out["chi_" + key] = chi
+        print(name, key, "max |u-u0| = %.3f" % np.abs(u - u0).max(), flush=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def make_fullsize_anchor():
+    """Method 0 on the whole clean/easy pair through the reference CLI: iteration
+    counts, EPE vs the Sintel ground truth, and a sub-sampled copy of the flow."""
+    import subprocess
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "clean_easy")
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "oracle", "_ref", "lib12"))
+    r = subprocess.run([po.REF_BIN, "ims.txt", "rg.flo", "var_m0.flo", "-m", "0", "-w", "5", "-verbose", "1"], cwd=D,
+                       env=env, capture_output=True, text=True, check=True)
+    iters = [int(l.split("Iter:")[1].split()[0]) for l in r.stderr.splitlines() if l.startswith("Warping:")]
+    var = po.read_flo(os.path.join(D, "var_m0.flo"))
+    rg = po.read_flo(os.path.join(D, "rg.flo"))
+    gt = po.read_flo(os.path.join(REF, "example_data", "clean", "easy", "gt", "frame_0002.flo"))
+    epe = lambda a: float(np.sqrt(((a - gt) ** 2).sum(0)).mean())
+    print("full-size m0 iters", iters, "EPE init %.4f -> %.4f" % (epe(rg), epe(var)))
+    np.savez_compressed(os.path.join(OUT, "fullsize_clean_easy_m0.npz"), iters=np.array(iters), epe_init=epe(rg),
+                        epe_out=epe(var), u_sub=var[:, ::8, ::8].copy(), gt_sub=gt[:, ::8, ::8].copy())
+
+
+if __name__ == "__main__":
+    assert po.have_ref(), "build the reference first: make -C oracle ref"
+    # 96x64 crop, every energy model (the reference always runs 400 iterations for methods 0-7)
+    make_case("crop_a", "clean/easy", 400, 200, 96, 64, [(0, 5, 400), (4, 2, 400), (2, 2, 400), (6, 2, 400), (8, 2, 30)])
+    # ragged size (w, h not multiples of 4 or of the tile), touching the image border region
+    make_case("crop_b", "clean/easy", 3, 5, 61, 45, [(0, 3, 400), (4, 1, 400), (2, 1, 400), (6, 1, 400), (8, 1, 12)])
+    make_fullsize_anchor()
