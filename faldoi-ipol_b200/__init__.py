@@ -44,7 +44,8 @@ _lib = None
 EXPORTS = [
     "faldoi_default_params", "faldoi_params_from_file", "faldoi_last_error", "faldoi_device_count",
     "faldoi_solver_create", "faldoi_solver_destroy", "faldoi_solver_upload", "faldoi_solver_run",
-    "faldoi_solver_sync", "faldoi_solver_download", "faldoi_solver_last_run_ms", "faldoi_solver_last_launches",
+    "faldoi_solver_sync", "faldoi_solver_download", "faldoi_solver_last_run_ms", "faldoi_solver_last_iter_ms",
+    "faldoi_solver_last_launches",
     "faldoi_solver_stream", "faldoi_solver_device_flow", "faldoi_global_solve", "faldoi_tvl2OF", "faldoi_tvcsad_PD",
     "faldoi_nltvl1_PD", "faldoi_nltvcsad_PD", "faldoi_guided_tvl2coupled_occ", "faldoi_centered_gradient",
     "faldoi_bicubic_warp",
@@ -61,6 +62,8 @@ def lib():
         L.faldoi_last_error.restype = C.c_char_p
         L.faldoi_solver_last_run_ms.restype = C.c_float
         L.faldoi_solver_last_launches.restype = C.c_longlong
+        L.faldoi_solver_last_iter_ms.restype = C.c_float
+        L.faldoi_solver_last_iter_ms.argtypes = [C.c_void_p]
         L.faldoi_solver_stream.restype = C.c_void_p
         L.faldoi_solver_device_flow.restype = C.c_void_p
         L.faldoi_solver_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -166,6 +169,10 @@ class Solver:
     @property
     def last_run_ms(self):
         return lib().faldoi_solver_last_run_ms(self._h)
+
+    @property
+    def last_iter_ms(self):
+        return lib().faldoi_solver_last_iter_ms(self._h)
 
     @property
     def last_launches(self):

@@ -135,6 +135,16 @@ float *faldoi_solver::dmalloc(size_t nfloats) {
     return (float *)p;
 }
 
+int faldoi_solver::phase_mark() {
+    if (phase_used == (int)phase_ev.size()) {
+        cudaEvent_t e;
+        FALDOI_CUDA(cudaEventCreate(&e));
+        phase_ev.push_back(e);
+    }
+    FALDOI_CUDA(cudaEventRecord(phase_ev[phase_used++], stream));
+    return FALDOI_OK;
+}
+
 int faldoi_solver::alloc_err(int max_iters) {
     if (max_iters <= err_cap) return FALDOI_OK;
     // (old arrays stay in `allocs` until destroy; growth happens at most a few times)
@@ -233,6 +243,7 @@ extern "C" void faldoi_solver_destroy(faldoi_solver *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (void *p : s->allocs) cudaFree(p);
+    for (cudaEvent_t e : s->phase_ev) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -241,7 +252,7 @@ extern "C" void faldoi_solver_destroy(faldoi_solver *s) {
 
 static int up2d(faldoi_solver *s, float *dst_plane, const float *src) {
     FALDOI_CUDA(cudaMemcpy2DAsync(dst_plane, s->g.pitch * sizeof(float), src, s->g.w * sizeof(float),
-                                  s->g.w * sizeof(float), s->g.h, cudaMemcpyHostToDevice, s->stream));
+                                  s->g.w * sizeof(float), s->g.h, cudaMemcpyDefault, s->stream));
     return FALDOI_OK;
 }
 
@@ -404,12 +415,14 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
             s->launches++;
         }
+        if (s->phase_mark()) return FALDOI_ERR_CUDA;
         for (int it = 0; it < p->max_iters; it++) {
             if (csad)
                 launch_tv_iter<DATA_CSAD>(s, a, it, npairs, R);
             else
                 launch_tv_iter<DATA_TVL1>(s, a, it, npairs, R);
         }
+        if (s->phase_mark()) return FALDOI_ERR_CUDA;
         s->launches += p->max_iters;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, 0, s->parity,
                                                                        s->log_iters, s->log_err, p->max_iters, a.tol2,
@@ -500,12 +513,14 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
             s->launches++;
         }
+        if (s->phase_mark()) return FALDOI_ERR_CUDA;
         for (int it = 0; it < p->max_iters; it++) {
             if (csad)
                 nltv_iter_kernel<DATA_CSAD><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
             else
                 nltv_iter_kernel<DATA_TVL1><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
         }
+        if (s->phase_mark()) return FALDOI_ERR_CUDA;
         s->launches += p->max_iters;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, 1, 1, s->parity, s->log_iters,
                                                                        s->log_err, p->max_iters, 0.f, (float)(g.w * g.h),
@@ -565,6 +580,7 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
         FALDOI_CUDA(cudaMemsetAsync(s->err_max, 0, (size_t)g.B * p->max_iters * sizeof(unsigned), s->stream));
         occ_warp_kernel<<<grd, blk, 0, s->stream>>>(a);
         s->launches++;
+        if (s->phase_mark()) return FALDOI_ERR_CUDA;
         for (int it = 0; it < p->max_iters; it++) {
             occ_v_kernel<<<grd, blk, 0, s->stream>>>(a, it);
             for (int k = 0; k < 24; k++) occ_xi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1);
@@ -572,6 +588,7 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
             for (int k = 0; k < 24; k++) occ_chi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1, k == 23);
             s->launches += 50;
         }
+        if (s->phase_mark()) return FALDOI_ERR_CUDA;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, 0, 0, nullptr, s->log_iters,
                                                                        s->log_err, p->max_iters, a.tol2, (float)(g.w * g.h),
                                                                        wp, npairs);
@@ -595,6 +612,7 @@ extern "C" int faldoi_solver_run(faldoi_solver *s, const faldoi_params *p, int n
     FALDOI_CUDA(cudaSetDevice(s->device));
     if (s->alloc_err(p->max_iters > 0 ? p->max_iters : 1) != FALDOI_OK) return FALDOI_ERR_MEM;
     s->launches = 0;
+    s->phase_used = 0;
     FALDOI_CUDA(cudaMemsetAsync(s->log_iters, 0, (size_t)s->B * FALDOI_MAX_WARPS * sizeof(int), s->stream));
     FALDOI_CUDA(cudaEventRecord(s->ev0, s->stream));
     int rc;
@@ -616,6 +634,10 @@ extern "C" int faldoi_solver_sync(faldoi_solver *s) {
     if (s->ran) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_ms = ms;
+        float acc = 0.f;
+        for (int i = 0; i + 1 < s->phase_used; i += 2)
+            if (cudaEventElapsedTime(&ms, s->phase_ev[i], s->phase_ev[i + 1]) == cudaSuccess) acc += ms;
+        s->last_iter_ms = acc;
     }
     return FALDOI_OK;
 }
@@ -627,9 +649,9 @@ extern "C" int faldoi_solver_download(faldoi_solver *s, int slot, float *u, floa
     }
     FALDOI_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)s->g.w * s->g.h;
-    FALDOI_CUDA(cudaMemcpyAsync(u, s->packed + (size_t)slot * 3 * n, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    FALDOI_CUDA(cudaMemcpyAsync(u, s->packed + (size_t)slot * 3 * n, 2 * n * sizeof(float), cudaMemcpyDefault, s->stream));
     if (chi && s->method == FALDOI_M_TVL1_OCC)
-        FALDOI_CUDA(cudaMemcpyAsync(chi, s->packed + (size_t)slot * 3 * n + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost,
+        FALDOI_CUDA(cudaMemcpyAsync(chi, s->packed + (size_t)slot * 3 * n + 2 * n, n * sizeof(float), cudaMemcpyDefault,
                                     s->stream));
     if (log) {
         FALDOI_CUDA(cudaMemcpyAsync(log->iters, s->log_iters + slot * FALDOI_MAX_WARPS, sizeof(log->iters),
@@ -641,6 +663,7 @@ extern "C" int faldoi_solver_download(faldoi_solver *s, int slot, float *u, floa
 }
 
 extern "C" float faldoi_solver_last_run_ms(faldoi_solver *s) { return s ? s->last_ms : -1.f; }
+extern "C" float faldoi_solver_last_iter_ms(faldoi_solver *s) { return s ? s->last_iter_ms : -1.f; }
 extern "C" long long faldoi_solver_last_launches(faldoi_solver *s) { return s ? s->launches : -1; }
 extern "C" void *faldoi_solver_stream(faldoi_solver *s) { return s ? (void *)s->stream : nullptr; }
 extern "C" float *faldoi_solver_device_flow(faldoi_solver *s, int slot, int *pitch_floats) {

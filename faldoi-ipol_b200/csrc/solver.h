@@ -55,9 +55,13 @@ struct faldoi_solver {
     float *packed = nullptr;
 
     float last_ms = 0.f;
+    float last_iter_ms = 0.f;             // time inside the per-iteration launches only
+    std::vector<cudaEvent_t> phase_ev;    // pairs (begin,end) around each warp's iteration loop
+    int phase_used = 0;
     long long launches = 0;
     bool ran = false;
 
     float *dmalloc(size_t nfloats);
+    int phase_mark();  // record the next phase event on the stream
     int alloc_err(int max_iters);
 };

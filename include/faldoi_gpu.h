@@ -76,7 +76,9 @@ int faldoi_device_count(void);
 int faldoi_solver_create(faldoi_solver **out, int device, int w, int h, int method, int batch);
 void faldoi_solver_destroy(faldoi_solver *s);
 
-/* Upload pair `slot` (0 <= slot < batch) from host memory.
+/* Upload pair `slot` (0 <= slot < batch).  Source pointers may be host memory (pageable or
+ * pinned) or device memory of the same GPU (copies use cudaMemcpyDefault); asynchronous on the
+ * handle's stream, so host buffers must stay valid until faldoi_solver_sync().
  *   I0,I1   preprocessed gray frames (w*h)
  *   Im1     preprocessed previous frame (w*h), method 8 only, else may be NULL
  *   lab     Lab image of I0 from image_to_lab (3*w*h planar), NLTV methods only, else NULL
@@ -99,6 +101,9 @@ int faldoi_solver_download(faldoi_solver *s, int slot, float *u, float *chi, fal
 
 /* Milliseconds the last faldoi_solver_run spent on the device (CUDA events on the handle's stream). */
 float faldoi_solver_last_run_ms(faldoi_solver *s);
+/* Of that, the milliseconds between the first and last per-iteration launch of every warp
+ * (i.e. excluding the bicubic warps / per-warp constants); valid after faldoi_solver_sync. */
+float faldoi_solver_last_iter_ms(faldoi_solver *s);
 /* Number of kernel launches issued by the last faldoi_solver_run. */
 long long faldoi_solver_last_launches(faldoi_solver *s);
 /* The handle's cudaStream_t (as void*) so callers can order their own work / events. */
