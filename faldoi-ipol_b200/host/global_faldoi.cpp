@@ -1,0 +1,230 @@
+// global_faldoi -- drop-in for the reference executable (src/global_faldoi.cpp:1846-2213):
+//
+//   global_faldoi ims.txt in_flow.flo out.flo [occ_in.png occ_out.png]
+//                 [-m method] [-w warps] [-p params.txt] [-glb_iters n] [-verbose 0|1]
+//
+// Same argv contract, file formats, method ids, parameter defaults and messages; the
+// minimisation itself (tvl2OF / nltvl1_PD / tvcsad_PD / nltvcsad_PD /
+// guided_tvl2coupled_occ) runs on a B200 through the C ABI in include/faldoi_gpu.h.
+// Extra option (ignored by the reference's scripts): -device d  (CUDA device, default 0).
+// There is no CPU fallback: without a usable GPU the program reports the error and fails.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/faldoi_gpu.h"
+#include "image_io.h"
+#include "preprocess.h"
+
+using faldoi_host::Image;
+
+namespace {
+
+// pick_option (src/utils_preprocess.cpp:21-35): "-name value" anywhere on the line,
+// removed from the vector; a trailing "-name" without a value is left in place.
+std::string pick_option(std::vector<std::string> &args, const std::string &option, const std::string &def) {
+    const std::string flag = "-" + option;
+    for (auto it = args.begin(); it != args.end(); ++it) {
+        if (*it == flag) {
+            if (it + 1 == args.end()) continue;
+            const std::string value = *(it + 1);
+            args.erase(it, it + 2);
+            return value;
+        }
+    }
+    return def;
+}
+
+void print_today() {
+    const std::time_t tt = std::chrono::system_clock::to_time_t(std::chrono::system_clock::now());
+    std::cerr << "today is: " << std::ctime(&tt);
+}
+
+void usage(size_t n) {
+    fprintf(stderr, "Without occlusions:\n");
+    fprintf(stderr, "Usage: %lu  ims.txt in_flow.flo  out.flo "
+                    "[-m method_val] [-w num_warps] [-p file of parameters] [-glb_iters global_iters] [-verbose verbose]"
+                    " \n", n);
+    fprintf(stderr, "With occlusions:\n");
+    fprintf(stderr, "Usage: %lu  ims.txt in_flow.flo  out.flo occl_input.png occl_out.png"
+                    " [-m method_val] [-w num_warps] [-p file of parameters] [-glb_iters global_iters] [-verbose verbose]"
+                    "\n", n);
+}
+
+const char *method_name(int m) {
+    switch (m) {
+        case FALDOI_M_NLTVL1: return "NLTV-L1";
+        case FALDOI_M_TVCSAD: return "TV-CSAD";
+        case FALDOI_M_NLTVCSAD: return "NLTV-CSAD";
+        case FALDOI_M_TVL1_W: return "TV-l2 coupled Weights";
+        case FALDOI_M_NLTVCSAD_W: return "NLTV-CSAD Weights";
+        case FALDOI_M_NLTVL1_W: return " NLTV-L1 Weights";
+        case FALDOI_M_TVCSAD_W: return "TV-CSAD Weights";
+        default: return "TV-l2 coupled";
+    }
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    print_today();
+    std::vector<std::string> args(argv, argv + argc);
+    const std::string warps_val = pick_option(args, "w", "5");
+    const std::string method_val = pick_option(args, "m", "0");
+    const std::string file_params = pick_option(args, "p", "");
+    const std::string global_iters = pick_option(args, "glb_iters", "400");
+    const std::string verbose_str = pick_option(args, "verbose", "0");
+    const std::string device_str = pick_option(args, "device", "0");
+
+    if (args.size() != 6 && args.size() != 4) {
+        usage(args.size());
+        return EXIT_FAILURE;
+    }
+
+    int val_method, nwarps, glb_it, device;
+    bool verbose;
+    try {
+        val_method = std::stoi(method_val);
+        nwarps = std::stoi(warps_val);
+        glb_it = std::stoi(global_iters);
+        device = std::stoi(device_str);
+        if (verbose_str != "0" && verbose_str != "1") throw std::invalid_argument("-verbose takes 0 or 1");
+        verbose = (verbose_str == "1");
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ERROR: bad option value (%s)\n", e.what());
+        return EXIT_FAILURE;
+    }
+
+    const std::string &filename_images = args[1];
+    const std::string &image_flow_name = args[2];
+    const std::string &outfile = args[3];
+    std::string occ_input, occ_output;
+    if (args.size() == 6) {
+        occ_input = args[4];
+        occ_output = args[5];
+    }
+
+    // ims.txt: line 1 = I0, line 2 = I1, line 3 = I-1, line 4 = I2 (unused)
+    std::string filename_i_1, filename_i0, filename_i1, line;
+    int num_files = 0;
+    {
+        std::ifstream infile(filename_images);
+        while (std::getline(infile, line)) {
+            ++num_files;
+            if (num_files == 1) filename_i0 = line;
+            if (num_files == 2) filename_i1 = line;
+            if (num_files == 3) filename_i_1 = line;
+        }
+    }
+
+    try {
+        // with fewer than 4 lines the reference reads I1 in place of I-1 (:1933-1937)
+        const Image i_1 = faldoi_host::read_image_split(num_files == 4 ? filename_i_1 : filename_i1);
+        const Image i0 = faldoi_host::read_image_split(filename_i0);
+        const Image i1 = faldoi_host::read_image_split(filename_i1);
+        const Image flow = faldoi_host::read_image_split(image_flow_name);
+        Image occ;
+        if (val_method >= 8) occ = faldoi_host::read_image_split(occ_input);
+
+        auto same = [](const Image &a, const Image &b) { return a.w == b.w && a.h == b.h && a.pd == b.pd; };
+        if (num_files == 3) {
+            if (!same(i0, i1) || !same(i0, i_1) || !same(i1, i_1))
+                return fprintf(stderr, "ERROR: input images and flow size mismatch\n");
+        } else if (!same(i0, i1)) {
+            return fprintf(stderr, "ERROR: input images and flow size mismatch\n");
+        }
+        if (i0.w != flow.w || i0.h != flow.h || flow.pd != 2) return fprintf(stderr, "ERROR: input flow field size mismatch\n");
+
+        if (num_files == 2 && val_method == FALDOI_M_TVL1_OCC) {
+            fprintf(stderr, "Since only two images given, method is changed to TV-l2 coupled\n");
+            fprintf(stderr, "Occlusion estimation requires 4 frames: i_1 ==> i0 ==> i1 ==> i2\n");
+            val_method = FALDOI_M_TVL1;
+        } else if (num_files == 4 && val_method >= 0 && val_method <= 7) {
+            fprintf(stderr, "Only two of the four images given will be used, according to the method selected\n");
+            fprintf(stderr, "Method: %s\n", method_name(val_method));
+        } else {
+            fprintf(stderr, "Method: ");
+            if (val_method == FALDOI_M_TVL1_OCC) fprintf(stderr, "TV-l2 occlusions\n");
+        }
+        if (val_method < 0 || val_method > 8) val_method = FALDOI_M_TVL1;  // the reference's dispatch falls through to nothing; we solve TVL2
+
+        const int w = i0.w, h = i0.h, pd = i0.pd;
+        const size_t size = (size_t)w * h;
+        if (val_method == FALDOI_M_TVL1_OCC && (occ.w != w || occ.h != h))
+            return fprintf(stderr, "ERROR: input images and flow size mismatch\n");
+
+        faldoi_params params;
+        if (faldoi_params_from_file(file_params.c_str(), val_method, glb_it, &params) != FALDOI_OK) {
+            fprintf(stderr, "ERROR: %s\n", faldoi_last_error());
+            return EXIT_FAILURE;
+        }
+        params.warps = nwarps;
+        if (verbose)
+            std::cerr << "Parameters: \n lambda: " << params.lambda << ", theta: " << params.theta << ", beta: " << params.beta
+                      << ", alpha: " << params.alpha << ", \n tau_u: " << params.tau_u << ", tau_eta: " << params.tau_eta
+                      << ", tau_chi: " << params.tau_chi << ", mu: " << params.mu << "\n";
+
+        const bool nltv = (val_method == FALDOI_M_NLTVL1 || val_method == FALDOI_M_NLTVL1_W ||
+                           val_method == FALDOI_M_NLTVCSAD || val_method == FALDOI_M_NLTVCSAD_W);
+        std::vector<float> lab;
+        if (nltv) {
+            std::printf("W:%d H:%d Pd:%d\n", w, h, pd);
+            if (pd < 3) {
+                fprintf(stderr, "ERROR: the NLTV models need a colour (3-channel) first frame\n");
+                return EXIT_FAILURE;
+            }
+            lab.resize(3 * size);
+            faldoi_host::image_to_lab(i0.data.data(), (int)size, lab.data());
+        }
+
+        std::vector<float> i0n(size), i1n(size), i_1n(size);
+        faldoi_host::preprocess(i0.data.data(), i1.data.data(), i_1.data.data(), pd, w, h, i0n.data(), i1n.data(), i_1n.data());
+
+        std::vector<float> u(flow.data);  // u1 | u2
+        std::vector<float> chi;
+        if (val_method >= 8) chi.assign(occ.data.begin(), occ.data.begin() + size);
+
+        if (nltv && (val_method == FALDOI_M_NLTVL1 || val_method == FALDOI_M_NLTVL1_W)) std::printf("Before\nInitialization\n");
+
+        const auto t0 = std::chrono::system_clock::now();
+        faldoi_log log{};
+        const int rc = faldoi_global_solve(device, &params, w, h, i0n.data(), i1n.data(), i_1n.data(), nltv ? lab.data() : nullptr,
+                                           u.data(), val_method >= 8 ? chi.data() : nullptr, &log);
+        if (rc != FALDOI_OK) {
+            fprintf(stderr, "ERROR: GPU solver failed (%d): %s\n", rc, faldoi_last_error());
+            return EXIT_FAILURE;
+        }
+        const std::chrono::duration<double> secs = std::chrono::system_clock::now() - t0;
+
+        if (verbose) {
+            for (int k = 0; k < params.warps; k++) {
+                if (val_method == FALDOI_M_TVL1_OCC)
+                    std::printf("Warping: %d, Iter: %d Error: %f\n", k, log.iters[k], log.err[k]);
+                else if (nltv)
+                    std::printf("Warping: %d,Iter: %d Error: %f\n", k, log.iters[k], log.err[k]);
+                else
+                    fprintf(stderr, "Warping: %d,Iter: %d Error: %f\n", k, log.iters[k], log.err[k]);
+            }
+        }
+        if (val_method == FALDOI_M_TVL1 || val_method == FALDOI_M_TVL1_W) std::cout << "(tvl2OF) All tasks took " << secs.count() << std::endl;
+        if (val_method == FALDOI_M_TVCSAD || val_method == FALDOI_M_TVCSAD_W) std::printf("Exits current level\n");
+
+        faldoi_host::write_image_float_split(outfile, u.data(), w, h, 2);
+        if (val_method == FALDOI_M_TVL1_OCC) {
+            std::vector<int> out_occ(size);
+            for (size_t i = 0; i < size; i++) out_occ[i] = (int)chi[i];
+            faldoi_host::write_png_gray8(occ_output, out_occ.data(), w, h);
+        }
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ERROR: %s\n", e.what());
+        return EXIT_FAILURE;
+    }
+    print_today();
+    return EXIT_SUCCESS;
+}

@@ -1,0 +1,165 @@
+"""Host side of the drop-in: libfaldoi_host.so (I/O + main()'s preprocessing) and the
+`global_faldoi` executable's argv contract.  CPU tests do not need a GPU; the end-to-end
+CLI runs are marked gpu."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_case
+
+PKG = os.path.join(ROOT, "faldoi-ipol_b200")
+BIN = os.path.join(PKG, "bin", "global_faldoi")
+HOST_SO = os.path.join(PKG, "libfaldoi_host.so")
+
+
+@pytest.fixture(scope="module")
+def H():
+    if not os.path.exists(HOST_SO) or not os.path.exists(BIN):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(PKG, "host")])
+    L = C.CDLL(HOST_SO)
+    L.faldoi_host_last_error.restype = C.c_char_p
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_host_exports(H):
+    txt = open(os.path.join(ROOT, "include", "faldoi_host.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(faldoi_host_[a-zA-Z0-9_]+)\s*\(", txt)))
+    assert len(syms) == 7
+    for s in syms:
+        assert hasattr(H, s), s
+
+
+@pytest.mark.parametrize("case", ["crop_a", "crop_b"])
+def test_host_preprocess_matches_reference(H, case):
+    g = load_case(case)
+    rgb = [np.ascontiguousarray(g[k].astype(np.float32)) for k in ("rgb_i0", "rgb_i1", "rgb_im1")]
+    _, h, w = rgb[0].shape
+    out = [np.empty((h, w), np.float32) for _ in range(3)]
+    assert H.faldoi_host_preprocess(_p(rgb[0]), _p(rgb[1]), _p(rgb[2]), 3, w, h, *[_p(o) for o in out]) == 0
+    assert np.array_equal(out[0], g["I0n"]) and np.array_equal(out[1], g["I1n"]) and np.array_equal(out[2], g["Im1n"])
+    lab = np.empty_like(rgb[0])
+    assert H.faldoi_host_image_to_lab(_p(rgb[0]), w, h, _p(lab)) == 0
+    assert np.array_equal(lab, g["lab"])
+
+
+def _read(H, path):
+    d, w, h, pd = C.POINTER(C.c_float)(), C.c_int(), C.c_int(), C.c_int()
+    rc = H.faldoi_host_read_image(path.encode(), C.byref(d), C.byref(w), C.byref(h), C.byref(pd))
+    if rc != 0:
+        raise RuntimeError(H.faldoi_host_last_error().decode())
+    a = np.ctypeslib.as_array(d, shape=(pd.value, h.value, w.value)).copy()
+    H.faldoi_host_free(d)
+    return a
+
+
+def test_image_io_roundtrips(H, tmp_path, po):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    # PNG written by PIL (all filter types appear with optimize) -> our decoder
+    for name, arr in (("rgb.png", rgb), ("gray.png", rgb[:, :, 0]), ("rgba.png", np.dstack([rgb, rgb[:, :, :1]]))):
+        Image.fromarray(arr).save(tmp_path / name, optimize=True)
+        a = _read(H, str(tmp_path / name))
+        want = arr if arr.ndim == 3 else arr[:, :, None]
+        assert np.array_equal(a, want.transpose(2, 0, 1).astype(np.float32)), name
+    Image.fromarray((rgb[:, :, 0].astype(np.uint16) * 257)).save(tmp_path / "g16.png")
+    assert np.array_equal(_read(H, str(tmp_path / "g16.png"))[0], rgb[:, :, 0].astype(np.float32) * 257)
+    po.write_ppm(str(tmp_path / "a.ppm"), rgb)
+    assert np.array_equal(_read(H, str(tmp_path / "a.ppm")), rgb.transpose(2, 0, 1).astype(np.float32))
+    # .flo both ways
+    u = rng.standard_normal((2, 37, 53)).astype(np.float32)
+    assert H.faldoi_host_write_flo(str(tmp_path / "u.flo").encode(), _p(u[0]), _p(u[1]), 53, 37) == 0
+    assert np.array_equal(po.read_flo(str(tmp_path / "u.flo")), u)
+    assert np.array_equal(_read(H, str(tmp_path / "u.flo")), u)
+    # occlusion mask PNG: values {0,1} in an 8-bit gray PNG, as iio_save_image_int writes it
+    m = (rng.random((37, 53)) > 0.5).astype(np.int32)
+    assert H.faldoi_host_write_png_gray8(str(tmp_path / "m.png").encode(), _p(m), 53, 37) == 0
+    im = Image.open(tmp_path / "m.png")
+    assert im.mode == "L" and np.array_equal(np.asarray(im), m.astype(np.uint8))
+    with pytest.raises(RuntimeError):
+        _read(H, str(tmp_path / "missing.png"))
+
+
+def _write_case(tmp_path, g, po, frames=4):
+    names = []
+    for k, key in enumerate(("rgb_i0", "rgb_i1", "rgb_im1", "rgb_i1")[:frames]):
+        p = str(tmp_path / ("f%d.ppm" % k))
+        po.write_ppm(p, np.ascontiguousarray(g[key].transpose(1, 2, 0)))
+        names.append(p)
+    (tmp_path / "ims.txt").write_text("\n".join(names) + "\n")
+    po.write_flo(str(tmp_path / "in.flo"), g["u0"])
+    return str(tmp_path / "ims.txt"), str(tmp_path / "in.flo")
+
+
+def test_cli_argv_contract(H, tmp_path, po):
+    # wrong number of positionals -> usage on stderr, EXIT_FAILURE (src/global_faldoi.cpp:1865-1876)
+    r = subprocess.run([BIN, "a", "b", "-m", "0"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr and "today is:" in r.stderr
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po)
+    # flow of the wrong size -> message + non-zero (:1961-1962)
+    po.write_flo(str(tmp_path / "bad.flo"), g["u0"][:, :-1])
+    r = subprocess.run([BIN, ims, str(tmp_path / "bad.flo"), str(tmp_path / "o.flo")], capture_output=True, text=True)
+    assert r.returncode != 0 and "input flow field size mismatch" in r.stderr
+    # -p <missing file>: the reference aborts in std::stof; we fail with a message
+    r = subprocess.run([BIN, ims, flo, str(tmp_path / "o.flo"), "-p", "0"], capture_output=True, text=True)
+    assert r.returncode != 0 and "parameter file" in r.stderr
+    # options may appear anywhere; on a box without a GPU the solve must FAIL, not fall back
+    r = subprocess.run([BIN, "-w", "1", ims, flo, "-m", "0", str(tmp_path / "o.flo")], capture_output=True, text=True)
+    fb_has_gpu = os.path.exists("/dev/nvidia0")
+    if not fb_has_gpu:
+        assert r.returncode != 0 and "GPU solver failed" in r.stderr and not os.path.exists(tmp_path / "o.flo")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,warps,iters", [(0, 3, 400), (4, 1, 400), (2, 1, 400), (8, 1, 12)])
+def test_cli_end_to_end(H, tmp_path, po, method, warps, iters):
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po)
+    out = str(tmp_path / "out.flo")
+    cmd = [BIN, ims, flo, out]
+    if method == 8:
+        from PIL import Image
+        Image.fromarray(g["chi0"].astype(np.uint8)).save(tmp_path / "occ_in.png")
+        cmd += [str(tmp_path / "occ_in.png"), str(tmp_path / "occ_out.png")]
+    cmd += ["-m", str(method), "-w", str(warps), "-glb_iters", str(iters), "-verbose", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    u = po.read_flo(out)
+    key = "m%d_w%d" % (method, warps) + ("_i%d" % iters if method == 8 else "")
+    if method in (0, 4, 8):
+        assert np.array_equal(u, g["u_" + key])
+    else:
+        d = np.abs(u - g["u_" + key])
+        assert d.mean() <= 1e-3 and d.max() <= 1e-2
+    log = r.stderr if method in (0, 4) else r.stdout
+    assert len(re.findall(r"Warping: \d+, ?Iter: \d+ Error: ", log)) == warps
+    if method == 0:
+        assert "(tvl2OF) All tasks took" in r.stdout
+    if method == 8:
+        from PIL import Image
+        m = np.asarray(Image.open(tmp_path / "occ_out.png"))
+        assert np.array_equal(m.astype(np.float32), g["chi_" + key])
+
+
+@pytest.mark.gpu
+def test_cli_two_frames_falls_back_from_occ(H, tmp_path, po):
+    """m=8 with a 2-line ims.txt -> notice + TV-l2 coupled (src/global_faldoi.cpp:1965-1973)."""
+    from PIL import Image
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po, frames=2)
+    Image.fromarray(g["chi0"].astype(np.uint8)).save(tmp_path / "occ_in.png")
+    out = str(tmp_path / "out.flo")
+    r = subprocess.run([BIN, ims, flo, out, str(tmp_path / "occ_in.png"), str(tmp_path / "occ_out.png"), "-m", "8", "-w", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "method is changed to TV-l2 coupled" in r.stderr
+    assert os.path.exists(out)
