@@ -9,6 +9,7 @@
 
 #include "solver.h"
 #include "tv_kernels.cuh"
+#include "tv_tile_kernel.cuh"
 #include "warp_kernels.cuh"
 #include "nltv_kernels.cuh"
 #include "occ_kernels.cuh"
@@ -127,12 +128,17 @@ extern "C" int faldoi_params_from_file(const char *path, int method, int glb_ite
 // ---------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------
+// Every device array carries a 1 KiB guard band on both sides: the tile kernels copy whole
+// 16-byte-aligned row segments including a 4-pixel halo left of column 0 / right of the last
+// tile, which for the first / last row of an array falls just outside it (never used in
+// arithmetic, but it must be addressable).
 float *faldoi_solver::dmalloc(size_t nfloats) {
+    const size_t guard = 256;  // floats
     void *p = nullptr;
-    if (!cuda_ok(cudaMalloc(&p, nfloats * sizeof(float)), "cudaMalloc")) return nullptr;
-    if (!cuda_ok(cudaMemsetAsync(p, 0, nfloats * sizeof(float), stream), "cudaMemset")) return nullptr;
+    if (!cuda_ok(cudaMalloc(&p, (nfloats + 2 * guard) * sizeof(float)), "cudaMalloc")) return nullptr;
+    if (!cuda_ok(cudaMemsetAsync(p, 0, (nfloats + 2 * guard) * sizeof(float), stream), "cudaMemset")) return nullptr;
     allocs.push_back(p);
-    return (float *)p;
+    return (float *)p + guard;
 }
 
 int faldoi_solver::phase_mark() {
@@ -329,8 +335,50 @@ static dim3 grid2d(const Geo &g, dim3 block, int npairs) {
     return dim3((g.w + block.x - 1) / block.x, (g.h + block.y - 1) / block.y, npairs);
 }
 
+// DivConst for x/theta: exhaustively verified on the device (2^23 significands) the first
+// time a theta value is seen by this handle; a failed verification just selects IEEE division.
+static int make_div_const(faldoi_solver *s, float b, DivConst *out) {
+    if (s->dc_valid && s->dc.b == b) {
+        *out = s->dc;
+        return FALDOI_OK;
+    }
+    DivConst d{b, 1.0f / b, 0};
+    if (!s->dc_flag) {
+        s->dc_flag = (int *)s->dmalloc(1);
+        if (!s->dc_flag) return FALDOI_ERR_MEM;
+    }
+    FALDOI_CUDA(cudaMemsetAsync(s->dc_flag, 0, sizeof(int), s->stream));
+    verify_div_const_kernel<<<(1u << 23) / 256, 256, 0, s->stream>>>(d.b, d.rb, s->dc_flag);
+    int mismatch = 1;
+    FALDOI_CUDA(cudaMemcpyAsync(&mismatch, s->dc_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    FALDOI_CUDA(cudaStreamSynchronize(s->stream));
+    d.ok = (mismatch == 0) ? 1 : 0;
+    s->dc = d;
+    s->dc_valid = true;
+    *out = d;
+    return FALDOI_OK;
+}
+
+static bool use_tile_kernel() {
+    static const bool v = [] {
+        const char *e = getenv("FALDOI_TV_KERNEL");  // "march" selects the register-marching kernel
+        return !(e && strcmp(e, "march") == 0);
+    }();
+    return v;
+}
+
 template <int DATA>
 static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
+    if (use_tile_kernel()) {
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[DATA]) {
+            cudaFuncSetAttribute(tv_tile_kernel<DATA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+            attr_set[DATA] = true;
+        }
+        const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
+        tv_tile_kernel<DATA><<<grid, 256, sizeof(TileSmem), s->stream>>>(a, it);
+        return;
+    }
     const dim3 block(32, 8);
     const int cols = (s->g.pitch + 127) / 128;
     if (R == 4)
@@ -343,6 +391,10 @@ static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs
 
 // rows per thread: as many as keep >= ~2 waves of 8-warp CTAs on 148 SMs
 static int pick_rows(const Geo &g, int npairs) {
+    if (const char *e = getenv("FALDOI_TV_ROWS")) {  // tuning knob for experiments
+        const int r = atoi(e);
+        if (r == 1 || r == 2 || r == 4) return r;
+    }
     const long warps1 = (long)((g.pitch + 127) / 128) * g.h * npairs;  // warps at R = 1
     if (warps1 / 4 >= 148L * 64) return 4;
     if (warps1 / 2 >= 148L * 64) return 2;
@@ -373,6 +425,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.theta = p->theta;
     a.l_t = p->lambda * p->theta;
     a.tol2 = p->tol * p->tol;
+    if (int rc = make_div_const(s, p->theta, &a.dth)) return rc;
     const int R = pick_rows(g, npairs);
     for (int wp = 0; wp < p->warps; wp++) {
         if (csad)
@@ -473,6 +526,7 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.tau = p->tau;
     a.theta = p->theta;
     a.l_t = p->lambda * p->theta;
+    if (int rc = make_div_const(s, p->theta, &a.dth)) return rc;
     int base_parity = 0;  // every pair runs all max_iters iterations: one parity for the batch
     FALDOI_CUDA(cudaMemsetAsync(s->parity, 0, (size_t)g.B * sizeof(int), s->stream));
     for (int wp = 0; wp < p->warps; wp++) {

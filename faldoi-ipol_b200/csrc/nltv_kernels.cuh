@@ -76,6 +76,7 @@ struct NlArgs {
     Geo g;
     int max_iters;
     float tau, theta, l_t;
+    DivConst dth;  // division by theta
 };
 
 // One fused NLTV iteration (:1249-1301 / :1729-1777): data-term v, dual update
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) nltv_iter_kernel(NlArgs a, int it, int ba
         const float *din = a.dual + (size_t)par * a.dual_set_stride + off;
         float *dout = a.dual + (size_t)(par ^ 1) * a.dual_set_stride + off;
         const int p = y * pitch + x;
-        const float tau = a.tau, theta = a.theta, l_t = a.l_t;
+        const float tau = a.tau, l_t = a.l_t;
         const float u1 = sin[ST_U1 * ks + p], u2 = sin[ST_U2 * ks + p];
         const float c1 = sin[ST_UB1 * ks + p], c2 = sin[ST_UB2 * ks + p];
         const float ix = a.Ix[off + p], iy = a.Iy[off + p];
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(256) nltv_iter_kernel(NlArgs a, int it, int ba
         dQ /= wtp;
 
         // ---- primal step (+div) and extrapolation ----
-        const float o1 = u1 - tau * (dP + (u1 - v1) / theta);
-        const float o2 = u2 - tau * (dQ + (u2 - v2) / theta);
+        const float o1 = u1 - tau * (dP + div_const(u1 - v1, a.dth));
+        const float o2 = u2 - tau * (dQ + div_const(u2 - v2, a.dth));
         esum = (double)((o1 - u1) * (o1 - u1) + (o2 - u2) * (o2 - u2));
         sout[ST_U1 * ks + p] = o1;
         sout[ST_U2 * ks + p] = o2;

@@ -54,6 +54,11 @@ struct faldoi_solver {
     // packed export buffer [B][3][h][w] (u1,u2,chi) for plain D2H copies
     float *packed = nullptr;
 
+    // verified constant-divisor (theta) fast division, cached per theta value
+    faldoi::DivConst dc{0.f, 0.f, 0};
+    bool dc_valid = false;
+    int *dc_flag = nullptr;
+
     float last_ms = 0.f;
     float last_iter_ms = 0.f;             // time inside the per-iteration launches only
     std::vector<cudaEvent_t> phase_ev;    // pairs (begin,end) around each warp's iteration loop

@@ -40,6 +40,7 @@ struct TvArgs {
     Geo g;
     int max_iters;
     float tau, theta, l_t, tol2;
+    DivConst dth;  // division by theta
 };
 
 // Has pair b already met the reference's exit test `err > tol^2` (false = stop)
@@ -81,6 +82,15 @@ __device__ __forceinline__ float csad_select(const float *__restrict__ bs, size_
     return ans;
 }
 
+// Norm used by TV-CSAD's row-wise projection, max(1, hypotf(a,b)) (tvcsad_getD :1433-1443).
+// Only values > 1 matter; a^2+b^2 evaluated in fp32 is within 3 ulp of the exact sum, so
+// below 0.999 the exact hypot is certainly <= 1 and the double-precision path is skipped.
+__device__ __forceinline__ float proj_norm_hypot(float a, float b) {
+    const float s = a * a + b * b;
+    if (s < 0.999f) return 1.f;
+    return hypotf_exact(a, b);
+}
+
 __device__ __forceinline__ int csad_count(int x, int y, int w, int h) {
     const int nx = min(x, 3) + min(w - 1 - x, 3) + 1;
     const int ny = min(y, 3) + min(h - 1 - y, 3) + 1;
@@ -88,7 +98,7 @@ __device__ __forceinline__ int csad_count(int x, int y, int w, int h) {
 }
 
 template <int R, int DATA>
-__global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
+__global__ void __launch_bounds__(256, 2) tv_iter_kernel(TvArgs a, int it) {
     const int b = blockIdx.z;
     if (!pair_active<DATA>(a, b, it)) return;
 
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
     float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
     const size_t ks = B * plane;  // stride between state kinds
     const float *cIx = a.Ix + (size_t)b * plane, *cIy = a.Iy + (size_t)b * plane;
-    const float tau = a.tau, theta = a.theta, l_t = a.l_t;
+    const float tau = a.tau, l_t = a.l_t;
 
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto LD = [&](const float *base, int row) -> float4 {
@@ -133,15 +143,19 @@ __global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const float u1y = b1[k] - u1a[k], u2y = b2[k] - u2a[k];  // yu < h-1 always
+            p12[k] = x12[k] + tau * u1y;
+            p22[k] = x22[k] + tau * u2y;
             if (DATA == DATA_TVL1) {
-                const float nrm = fmaxf(1.f, sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]));
-                p12[k] = (x12[k] + tau * u1y) / nrm;
-                p22[k] = (x22[k] + tau * u2y) / nrm;
+                const float nrm = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
+                if (nrm > 1.f) {
+                    p12[k] /= nrm;
+                    p22[k] /= nrm;
+                }
             } else {
-                const float n1 = fmaxf(1.f, hypotf_exact(x11[k], x12[k]));
-                const float n2 = fmaxf(1.f, hypotf_exact(x21[k], x22[k]));
-                p12[k] = (x12[k] + tau * u1y) / n1;
-                p22[k] = (x22[k] + tau * u2y) / n2;
+                const float n1 = proj_norm_hypot(x11[k], x12[k]);
+                const float n2 = proj_norm_hypot(x21[k], x22[k]);
+                if (n1 > 1.f) p12[k] /= n1;
+                if (n2 > 1.f) p22[k] /= n2;
             }
         }
     }
@@ -194,19 +208,30 @@ __global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
             const float u2x = (gx < w - 1) ? b2[k + 1] - b2[k] : 0.f;
             const float u1y = ylast ? 0.f : n1r[k] - b1[k];
             const float u2y = ylast ? 0.f : n2r[k] - b2[k];
+            // x / max(1,|xi_old|): the divisor is exactly 1 wherever |xi_old| <= 1 (x/1 == x)
+            m11[k] = x11[k] + tau * u1x;
+            m12[k] = x12[k] + tau * u1y;
+            m21[k] = x21[k] + tau * u2x;
+            m22[k] = x22[k] + tau * u2y;
             if (DATA == DATA_TVL1) {
-                const float nrm = fmaxf(1.f, sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]));
-                m11[k] = (x11[k] + tau * u1x) / nrm;
-                m12[k] = (x12[k] + tau * u1y) / nrm;
-                m21[k] = (x21[k] + tau * u2x) / nrm;
-                m22[k] = (x22[k] + tau * u2y) / nrm;
+                const float nrm = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
+                if (nrm > 1.f) {
+                    m11[k] /= nrm;
+                    m12[k] /= nrm;
+                    m21[k] /= nrm;
+                    m22[k] /= nrm;
+                }
             } else {
-                const float n1 = fmaxf(1.f, hypotf_exact(x11[k], x12[k]));
-                const float n2 = fmaxf(1.f, hypotf_exact(x21[k], x22[k]));
-                m11[k] = (x11[k] + tau * u1x) / n1;
-                m12[k] = (x12[k] + tau * u1y) / n1;
-                m21[k] = (x21[k] + tau * u2x) / n2;
-                m22[k] = (x22[k] + tau * u2y) / n2;
+                const float n1 = proj_norm_hypot(x11[k], x12[k]);
+                const float n2 = proj_norm_hypot(x21[k], x22[k]);
+                if (n1 > 1.f) {
+                    m11[k] /= n1;
+                    m12[k] /= n1;
+                }
+                if (n2 > 1.f) {
+                    m21[k] /= n2;
+                    m22[k] /= n2;
+                }
             }
         }
 
@@ -219,13 +244,18 @@ __global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
             const float e21 = in[ST_XI21 * ks + o], e22 = in[ST_XI22 * ks + o];
             const float c1 = in[ST_UB1 * ks + o], c2 = in[ST_UB2 * ks + o];
             const float u1x = b1[0] - c1, u2x = b2[0] - c2;  // x-1 < w-1 always
+            l11 = e11 + tau * u1x;
+            l21 = e21 + tau * u2x;
             if (DATA == DATA_TVL1) {
-                const float nrm = fmaxf(1.f, sqrtf(e11 * e11 + e12 * e12 + e21 * e21 + e22 * e22));
-                l11 = (e11 + tau * u1x) / nrm;
-                l21 = (e21 + tau * u2x) / nrm;
+                const float nrm = sqrtf(e11 * e11 + e12 * e12 + e21 * e21 + e22 * e22);
+                if (nrm > 1.f) {
+                    l11 /= nrm;
+                    l21 /= nrm;
+                }
             } else {
-                l11 = (e11 + tau * u1x) / fmaxf(1.f, hypotf_exact(e11, e12));
-                l21 = (e21 + tau * u2x) / fmaxf(1.f, hypotf_exact(e21, e22));
+                const float n1 = proj_norm_hypot(e11, e12), n2 = proj_norm_hypot(e21, e22);
+                if (n1 > 1.f) l11 /= n1;
+                if (n2 > 1.f) l21 /= n2;
             }
         }
 
@@ -269,8 +299,8 @@ __global__ void __launch_bounds__(256) tv_iter_kernel(TvArgs a, int it) {
                 }
             }
             // primal step (ofTVl2_getP :325-335) and extrapolation (:780-783)
-            o1[k] = u1[k] - tau * (-d1 + (u1[k] - v1) / theta);
-            o2[k] = u2[k] - tau * (-d2 + (u2[k] - v2) / theta);
+            o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
+            o2[k] = u2[k] - tau * (-d2 + div_const(u2[k] - v2, a.dth));
             const float e = (o1[k] - u1[k]) * (o1[k] - u1[k]) + (o2[k] - u2[k]) * (o2[k] - u2[k]);
             if (gx < w) {
                 emax = fmaxf(emax, e);

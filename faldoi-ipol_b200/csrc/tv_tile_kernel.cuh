@@ -1,0 +1,271 @@
+// Shared-memory tiled version of the fused TV iteration (same math and interface as
+// tv_iter_kernel in tv_kernels.cuh; see there for the reference citations).
+//
+// One CTA = one 128 x 16 pixel tile of one pair.  All 11 input planes of the tile are
+// staged into shared memory with the bulk async-copy engine (cp.async.bulk ->
+// UBLKCP, one 16-byte-aligned row segment per copy, completion on an mbarrier), so no
+// registers are held while HBM latency is outstanding and two CTAs per SM overlap one
+// tile's loads with the other's arithmetic:
+//   ubar1,ubar2     rows y0-1 .. y0+16, cols x0-4 .. x0+131   (forward differences + halo)
+//   xi11..xi22      rows y0-1 .. y0+15, cols x0-4 .. x0+131   (old duals incl. top/left halo)
+//   u1,u2,c0,Ix,Iy  rows y0   .. y0+15, cols x0   .. x0+127   (c0 = rho_c or the CSAD scale)
+// phase 1: xi_new on the tile plus its top row and left column, in place in smem
+// phase 2: divergence from smem, data term, primal step, extrapolation, error; the 8 output
+//          planes go straight to HBM as float4.
+// Out-of-image halo rows / columns are never read by the boundary-aware stencils; the row
+// copies that would fall outside the plane are skipped (rows) or land in the allocation's
+// guard bands (columns), see faldoi_solver_create.
+#pragma once
+#include "common.cuh"
+#include "tv_kernels.cuh"
+
+namespace faldoi {
+
+enum { TT_W = 128, TT_H = 16, TT_PW = TT_W + 8 };  // tile size, padded smem row (cols x0-4 .. x0+131)
+
+struct TileSmem {
+    float ub[2][TT_H + 2][TT_PW];  // rows y0-1 .. y0+16
+    float xi[4][TT_H + 1][TT_PW];  // rows y0-1 .. y0+15
+    float pl[5][TT_H][TT_W];       // u1, u2, c0, Ix, Iy
+    float red[8];
+    double redd[8];
+    unsigned long long bar;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_row(void *dst_smem, const float *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int DATA>
+__global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+    const int b = blockIdx.z;
+    if (!pair_active<DATA>(a, b, it)) return;
+
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    const int x0 = blockIdx.x * TT_W, y0 = blockIdx.y * TT_H;
+    const int tid = threadIdx.x;
+    const int rows = min(TT_H, h - y0);  // interior rows of this tile that exist
+
+    const int par = (a.parity[b] + it) & 1;
+    const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
+    const float *in = a.state + (size_t)par * a.set_stride + (size_t)b * plane;
+    float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
+    const float *c0 = (DATA == DATA_TVL1 ? a.rho_c : a.scale) + (size_t)b * plane;
+    const float *cIx = a.Ix + (size_t)b * plane, *cIy = a.Iy + (size_t)b * plane;
+
+    // ---- stage the tile: thread 0 arms the barrier, then one row segment per thread ----
+    const int ub_lo = (y0 > 0) ? -1 : 0, ub_hi = min(TT_H, h - 1 - y0);  // ubar rows (relative) lo..hi inclusive
+    const int xi_lo = ub_lo, xi_hi = rows - 1;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        const unsigned total = (unsigned)(2 * (ub_hi - ub_lo + 1) + 4 * (xi_hi - xi_lo + 1)) * TT_PW * 4u + (unsigned)(5 * rows) * TT_W * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"(total) : "memory");
+    }
+    __syncthreads();
+    {
+        // job list: [0, 2*18) ubar rows, [36, 36+4*17) xi rows, [104, 104+5*16) plain rows
+        for (int j = tid; j < 2 * (TT_H + 2) + 4 * (TT_H + 1) + 5 * TT_H; j += 256) {
+            if (j < 2 * (TT_H + 2)) {
+                const int k = j / (TT_H + 2), r = j % (TT_H + 2) - 1;
+                if (r >= ub_lo && r <= ub_hi)
+                    bulk_row(&S.ub[k][r + 1][0], in + (ST_UB1 + k) * ks + (size_t)(y0 + r) * pitch + x0 - 4, TT_PW * 4, &S.bar);
+            } else if (j < 2 * (TT_H + 2) + 4 * (TT_H + 1)) {
+                const int jj = j - 2 * (TT_H + 2);
+                const int k = jj / (TT_H + 1), r = jj % (TT_H + 1) - 1;
+                if (r >= xi_lo && r <= xi_hi)
+                    bulk_row(&S.xi[k][r + 1][0], in + (ST_XI11 + k) * ks + (size_t)(y0 + r) * pitch + x0 - 4, TT_PW * 4, &S.bar);
+            } else {
+                const int jj = j - 2 * (TT_H + 2) - 4 * (TT_H + 1);
+                const int k = jj / TT_H, r = jj % TT_H;
+                if (r < rows) {
+                    const float *src = (k == 0) ? in + ST_U1 * ks : (k == 1) ? in + ST_U2 * ks : (k == 2) ? c0 : (k == 3) ? cIx : cIy;
+                    bulk_row(&S.pl[k][r][0], src + (size_t)(y0 + r) * pitch + x0, TT_W * 4, &S.bar);
+                }
+            }
+        }
+    }
+    // wait for the bytes (phase 0)
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(smem_u32(&S.bar)), "r"(0)
+                : "memory");
+        }
+    }
+
+    const float tau = a.tau, l_t = a.l_t;
+
+    // ---- phase 1: dual step on rows -1..rows-1 (relative), column quads -1..31 (quad -1 = cols x0-4..x0-1) ----
+    for (int t = tid; t < (TT_H + 1) * 33; t += 256) {
+        const int r = t / 33 - 1, q = t % 33 - 1;
+        if (r < xi_lo || r > xi_hi) continue;
+        const int y = y0 + r, cx = 4 * (q + 1);  // smem column of the quad's first pixel
+        const int gx0 = x0 + 4 * q;
+        if (gx0 + 3 < 0 || gx0 >= w) continue;
+        const bool ylast = (y == h - 1);
+        const float4 B1 = *reinterpret_cast<const float4 *>(&S.ub[0][r + 1][cx]);
+        const float4 B2 = *reinterpret_cast<const float4 *>(&S.ub[1][r + 1][cx]);
+        const float b1[5] = {B1.x, B1.y, B1.z, B1.w, S.ub[0][r + 1][cx + 4]};
+        const float b2[5] = {B2.x, B2.y, B2.z, B2.w, S.ub[1][r + 1][cx + 4]};
+        float4 N1 = make_float4(0.f, 0.f, 0.f, 0.f), N2 = N1;
+        if (!ylast) {
+            N1 = *reinterpret_cast<const float4 *>(&S.ub[0][r + 2][cx]);
+            N2 = *reinterpret_cast<const float4 *>(&S.ub[1][r + 2][cx]);
+        }
+        const float n1[4] = {N1.x, N1.y, N1.z, N1.w}, n2[4] = {N2.x, N2.y, N2.z, N2.w};
+        float4 X11 = *reinterpret_cast<const float4 *>(&S.xi[0][r + 1][cx]);
+        float4 X12 = *reinterpret_cast<const float4 *>(&S.xi[1][r + 1][cx]);
+        float4 X21 = *reinterpret_cast<const float4 *>(&S.xi[2][r + 1][cx]);
+        float4 X22 = *reinterpret_cast<const float4 *>(&S.xi[3][r + 1][cx]);
+        float x11[4] = {X11.x, X11.y, X11.z, X11.w}, x12[4] = {X12.x, X12.y, X12.z, X12.w};
+        float x21[4] = {X21.x, X21.y, X21.z, X21.w}, x22[4] = {X22.x, X22.y, X22.z, X22.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = gx0 + k;
+            const float u1x = (gx < w - 1) ? b1[k + 1] - b1[k] : 0.f;
+            const float u2x = (gx < w - 1) ? b2[k + 1] - b2[k] : 0.f;
+            const float u1y = ylast ? 0.f : n1[k] - b1[k];
+            const float u2y = ylast ? 0.f : n2[k] - b2[k];
+            if (DATA == DATA_TVL1) {
+                const float nrm = fmaxf(1.f, sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]));
+                x11[k] = (x11[k] + tau * u1x) / nrm;
+                x12[k] = (x12[k] + tau * u1y) / nrm;
+                x21[k] = (x21[k] + tau * u2x) / nrm;
+                x22[k] = (x22[k] + tau * u2y) / nrm;
+            } else {
+                const float m1 = fmaxf(1.f, proj_norm_hypot(x11[k], x12[k]));
+                const float m2 = fmaxf(1.f, proj_norm_hypot(x21[k], x22[k]));
+                x11[k] = (x11[k] + tau * u1x) / m1;
+                x12[k] = (x12[k] + tau * u1y) / m1;
+                x21[k] = (x21[k] + tau * u2x) / m2;
+                x22[k] = (x22[k] + tau * u2y) / m2;
+            }
+        }
+        *reinterpret_cast<float4 *>(&S.xi[0][r + 1][cx]) = make_float4(x11[0], x11[1], x11[2], x11[3]);
+        *reinterpret_cast<float4 *>(&S.xi[1][r + 1][cx]) = make_float4(x12[0], x12[1], x12[2], x12[3]);
+        *reinterpret_cast<float4 *>(&S.xi[2][r + 1][cx]) = make_float4(x21[0], x21[1], x21[2], x21[3]);
+        *reinterpret_cast<float4 *>(&S.xi[3][r + 1][cx]) = make_float4(x22[0], x22[1], x22[2], x22[3]);
+    }
+    __syncthreads();
+
+    // ---- phase 2: divergence, data term, primal step, extrapolation ----
+    float emax = 0.f;
+    double esum = 0.0;
+    for (int t = tid; t < TT_H * 32; t += 256) {
+        const int r = t >> 5, q = t & 31;
+        if (r >= rows) continue;
+        const int y = y0 + r, cx = 4 * (q + 1), gx0 = x0 + 4 * q;
+        if (gx0 >= pitch) continue;
+        const float4 M11 = *reinterpret_cast<const float4 *>(&S.xi[0][r + 1][cx]);
+        const float4 M12 = *reinterpret_cast<const float4 *>(&S.xi[1][r + 1][cx]);
+        const float4 M21 = *reinterpret_cast<const float4 *>(&S.xi[2][r + 1][cx]);
+        const float4 M22 = *reinterpret_cast<const float4 *>(&S.xi[3][r + 1][cx]);
+        const float4 T12 = *reinterpret_cast<const float4 *>(&S.xi[1][r][cx]);
+        const float4 T22 = *reinterpret_cast<const float4 *>(&S.xi[3][r][cx]);
+        const float l11 = S.xi[0][r + 1][cx - 1], l21 = S.xi[2][r + 1][cx - 1];
+        const float4 U1 = *reinterpret_cast<const float4 *>(&S.pl[0][r][4 * q]);
+        const float4 U2 = *reinterpret_cast<const float4 *>(&S.pl[1][r][4 * q]);
+        const float4 C0 = *reinterpret_cast<const float4 *>(&S.pl[2][r][4 * q]);
+        const float4 IX = *reinterpret_cast<const float4 *>(&S.pl[3][r][4 * q]);
+        const float4 IY = *reinterpret_cast<const float4 *>(&S.pl[4][r][4 * q]);
+        const float m11[4] = {M11.x, M11.y, M11.z, M11.w}, m12[4] = {M12.x, M12.y, M12.z, M12.w};
+        const float m21[4] = {M21.x, M21.y, M21.z, M21.w}, m22[4] = {M22.x, M22.y, M22.z, M22.w};
+        const float p12[4] = {T12.x, T12.y, T12.z, T12.w}, p22[4] = {T22.x, T22.y, T22.z, T22.w};
+        const float u1[4] = {U1.x, U1.y, U1.z, U1.w}, u2[4] = {U2.x, U2.y, U2.z, U2.w};
+        const float cc[4] = {C0.x, C0.y, C0.z, C0.w};
+        const float ix[4] = {IX.x, IX.y, IX.z, IX.w}, iy[4] = {IY.x, IY.y, IY.z, IY.w};
+        float o1[4], o2[4], ob1[4], ob2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = gx0 + k;
+            const float d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, y, w, h);
+            const float d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, y, w, h);
+            float v1, v2;
+            if (DATA == DATA_TVL1) {
+                const float grad = ix[k] * ix[k] + iy[k] * iy[k];
+                const float rho = cc[k] + (ix[k] * u1[k] + iy[k] * u2[k]);
+                float e1, e2;
+                if (rho < -l_t * grad) {
+                    e1 = l_t * ix[k];
+                    e2 = l_t * iy[k];
+                } else if (rho > l_t * grad) {
+                    e1 = -l_t * ix[k];
+                    e2 = -l_t * iy[k];
+                } else if (grad_is_zero(grad)) {
+                    e1 = e2 = 0.f;
+                } else {
+                    const float fi = -rho / grad;
+                    e1 = fi * ix[k];
+                    e2 = fi * iy[k];
+                }
+                v1 = u1[k] + e1;
+                v2 = u2[k] + e2;
+            } else {
+                v1 = u1[k];
+                v2 = u2[k];
+                if (gx < w) {
+                    const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / cc[k];
+                    const int np = csad_count(gx, y, w, h);
+                    const float med = csad_select(a.bs + (size_t)b * plane + (size_t)y * pitch + gx, ks, np, s, l_t, cc[k]);
+                    v1 = u1[k] - ix[k] * med / cc[k];
+                    v2 = u2[k] - iy[k] * med / cc[k];
+                }
+            }
+            o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
+            o2[k] = u2[k] - tau * (-d2 + div_const(u2[k] - v2, a.dth));
+            const float e = (o1[k] - u1[k]) * (o1[k] - u1[k]) + (o2[k] - u2[k]) * (o2[k] - u2[k]);
+            if (gx < w) {
+                emax = fmaxf(emax, e);
+                if (DATA == DATA_CSAD) esum += (double)e;
+            }
+            ob1[k] = 2 * o1[k] - u1[k];
+            ob2[k] = 2 * o2[k] - u2[k];
+        }
+        const size_t o = (size_t)y * pitch + gx0;
+        st4(out + ST_XI11 * ks + o, M11);
+        st4(out + ST_XI12 * ks + o, M12);
+        st4(out + ST_XI21 * ks + o, M21);
+        st4(out + ST_XI22 * ks + o, M22);
+        st4(out + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+        st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+        st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+    }
+
+    // ---- convergence measure ----
+    const int lane = tid & 31, wid = tid >> 5;
+    if (DATA == DATA_TVL1) {
+        emax = warp_max(emax);
+        if (lane == 0) S.red[wid] = emax;
+    } else {
+        esum = warp_sum(esum);
+        if (lane == 0) S.redd[wid] = esum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (DATA == DATA_TVL1) {
+            float m = S.red[0];
+            for (int i = 1; i < 8; i++) m = fmaxf(m, S.red[i]);
+            atomicMax(a.err_max + (size_t)b * a.max_iters + it, __float_as_uint(m));
+        } else {
+            double t = S.redd[0];
+            for (int i = 1; i < 8; i++) t += S.redd[i];
+            atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
+        }
+    }
+}
+
+}  // namespace faldoi
