@@ -48,7 +48,9 @@ EXPORTS = [
     "faldoi_solver_last_launches",
     "faldoi_solver_stream", "faldoi_solver_device_flow", "faldoi_global_solve", "faldoi_tvl2OF", "faldoi_tvcsad_PD",
     "faldoi_nltvl1_PD", "faldoi_nltvcsad_PD", "faldoi_guided_tvl2coupled_occ", "faldoi_centered_gradient",
-    "faldoi_bicubic_warp",
+    "faldoi_bicubic_warp", "faldoi_stripe_rows", "faldoi_stripes_create", "faldoi_stripes_destroy",
+    "faldoi_stripes_upload", "faldoi_stripes_run", "faldoi_stripes_download", "faldoi_stripes_last_run_ms",
+    "faldoi_stripes_last_launches",
 ]
 
 
@@ -87,6 +89,16 @@ def lib():
         L.faldoi_guided_tvl2coupled_occ.argtypes = [vp] * 6 + [C.POINTER(Params), i, i, i]
         L.faldoi_centered_gradient.argtypes = [i] + [vp] * 3 + [i, i]
         L.faldoi_bicubic_warp.argtypes = [i] + [vp] * 4 + [i, i, i]
+        L.faldoi_stripe_rows.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+        L.faldoi_stripes_create.argtypes = [C.POINTER(vp), i, C.POINTER(i), i, i, i]
+        L.faldoi_stripes_destroy.argtypes = [vp]
+        L.faldoi_stripes_upload.argtypes = [vp, vp, vp, vp]
+        L.faldoi_stripes_run.argtypes = [vp, C.POINTER(Params)]
+        L.faldoi_stripes_download.argtypes = [vp, vp, C.POINTER(Log)]
+        L.faldoi_stripes_last_run_ms.argtypes = [vp]
+        L.faldoi_stripes_last_run_ms.restype = C.c_float
+        L.faldoi_stripes_last_launches.argtypes = [vp]
+        L.faldoi_stripes_last_launches.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -181,6 +193,61 @@ class Solver:
     @property
     def stream(self):
         return lib().faldoi_solver_stream(self._h)
+
+
+def stripe_rows(h, nstripes, k):
+    """Rows [row0, row1) of a frame of height h owned by stripe k of nstripes (faldoi_stripe_rows)."""
+    r0, r1 = C.c_int(), C.c_int()
+    _check(lib().faldoi_stripe_rows(h, nstripes, k, C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+class Stripes:
+    """One large frame pair cut into row stripes over several GPUs (faldoi_stripes_*), TVL2."""
+
+    def __init__(self, w, h, devices, method=M_TVL1):
+        self._h = C.c_void_p()
+        self.w, self.h, self.devices = w, h, list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(lib().faldoi_stripes_create(C.byref(self._h), len(self.devices), arr, w, h, method))
+
+    def close(self):
+        if self._h:
+            lib().faldoi_stripes_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, I0, I1, u):
+        arrs = [_f32(x) for x in (I0, I1, u)]
+        _check(lib().faldoi_stripes_upload(self._h, *[_ptr(x) for x in arrs]))
+
+    def upload_ptrs(self, I0, I1, u):
+        _check(lib().faldoi_stripes_upload(self._h, I0, I1, u))
+
+    def run(self, params):
+        _check(lib().faldoi_stripes_run(self._h, C.byref(params)))
+
+    def download(self):
+        u = np.empty((2, self.h, self.w), np.float32)
+        log = Log()
+        _check(lib().faldoi_stripes_download(self._h, _ptr(u), C.byref(log)))
+        return u, log
+
+    def download_ptr(self, u_ptr):
+        _check(lib().faldoi_stripes_download(self._h, u_ptr, None))
+
+    @property
+    def last_run_ms(self):
+        return lib().faldoi_stripes_last_run_ms(self._h)
+
+    @property
+    def last_launches(self):
+        return lib().faldoi_stripes_last_launches(self._h)
 
 
 def global_solve(method, I0, I1, u, Im1=None, lab=None, chi=None, params=None, warps=5, glb_iters=400, device=0):

@@ -161,7 +161,16 @@ int faldoi_solver::alloc_err(int max_iters) {
     return FALDOI_OK;
 }
 
+struct StripeGeo {
+    int y_off, hg, own_lo, own_hi;
+};
+static int create_internal(faldoi_solver **out, int device, int w, int h, int method, int batch, const StripeGeo *sg);
+
 extern "C" int faldoi_solver_create(faldoi_solver **out, int device, int w, int h, int method, int batch) {
+    return create_internal(out, device, w, h, method, batch, nullptr);
+}
+
+static int create_internal(faldoi_solver **out, int device, int w, int h, int method, int batch, const StripeGeo *sg) {
     if (!out || w < 2 || h < 2 || batch < 1 || method < 0 || method > 8) {
         set_error("faldoi_solver_create: bad argument");
         return FALDOI_ERR_ARG;
@@ -183,11 +192,12 @@ extern "C" int faldoi_solver_create(faldoi_solver **out, int device, int w, int 
     s->device = device;
     s->method = method;
     s->B = batch;
-    s->g.w = w;
-    s->g.h = h;
-    s->g.pitch = (w + 31) / 32 * 32;
-    s->g.B = batch;
-    s->g.plane = (size_t)s->g.pitch * h;
+    s->g = make_geo(w, h, (w + 31) / 32 * 32, batch);
+    s->i1_plane = s->g.plane;
+    if (sg) {  // row stripe of a taller frame: I1 and its gradients stay full frames (the warp samples any row)
+        s->g.y_off = sg->y_off, s->g.hg = sg->hg, s->g.own_lo = sg->own_lo, s->g.own_hi = sg->own_hi;
+        s->i1_plane = (size_t)s->g.pitch * sg->hg;
+    }
     const size_t P = s->g.plane, B = batch;
     auto fail = [&](int code) {
         faldoi_solver_destroy(s);
@@ -204,9 +214,9 @@ extern "C" int faldoi_solver_create(faldoi_solver **out, int device, int w, int 
     } while (0)
 
     ALLOC(s->I0, B * P);
-    ALLOC(s->I1, B * P);
-    ALLOC(s->I1x, B * P);
-    ALLOC(s->I1y, B * P);
+    ALLOC(s->I1, B * s->i1_plane);
+    ALLOC(s->I1x, B * s->i1_plane);
+    ALLOC(s->I1y, B * s->i1_plane);
     ALLOC(s->packed, B * 3 * (size_t)w * h);
     s->parity = (int *)s->dmalloc(B);
     s->log_iters = (int *)s->dmalloc(B * FALDOI_MAX_WARPS);
@@ -417,6 +427,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.scale = s->scale;
     a.bs = s->bs;
     a.err_max = s->err_max;
+    a.err_chk = s->err_max;
     a.err_sum = s->err_sum;
     a.parity = s->parity;
     a.g = g;
@@ -437,6 +448,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         wa.I1 = s->I1;
         wa.I1x = s->I1x;
         wa.I1y = s->I1y;
+        wa.i1_plane = s->i1_plane;
         wa.u1 = s->state + ST_U1 * ks;
         wa.u2 = s->state + ST_U2 * ks;
         wa.ub1 = s->state + ST_UB1 * ks;
@@ -536,6 +548,7 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         wa.I1 = s->I1;
         wa.I1x = s->I1x;
         wa.I1y = s->I1y;
+        wa.i1_plane = s->i1_plane;
         wa.u1 = s->state + ST_U1 * ks;
         wa.u2 = s->state + ST_U2 * ks;
         wa.ub1 = s->state + ST_UB1 * ks;
@@ -872,7 +885,7 @@ struct Scratch {
 extern "C" int faldoi_centered_gradient(int device, const float *in, float *dx, float *dy, int nx, int ny) {
     if (!in || !dx || !dy || nx < 2 || ny < 2) return FALDOI_ERR_ARG;
     FALDOI_CUDA(cudaSetDevice(device));
-    Geo g{nx, ny, nx, 1, (size_t)nx * ny};
+    Geo g = make_geo(nx, ny, nx, 1);
     Scratch sc;
     float *d_in = sc.get(g.plane), *d_dx = sc.get(g.plane), *d_dy = sc.get(g.plane);
     if (!d_in || !d_dx || !d_dy) return FALDOI_ERR_MEM;
@@ -889,7 +902,7 @@ extern "C" int faldoi_bicubic_warp(int device, const float *in, const float *u, 
                                    int ny, int border_out) {
     if (!in || !u || !v || !out || nx < 1 || ny < 1) return FALDOI_ERR_ARG;
     FALDOI_CUDA(cudaSetDevice(device));
-    Geo g{nx, ny, nx, 1, (size_t)nx * ny};
+    Geo g = make_geo(nx, ny, nx, 1);
     Scratch sc;
     float *d_in = sc.get(g.plane), *d_u = sc.get(g.plane), *d_v = sc.get(g.plane), *d_o = sc.get(g.plane);
     if (!d_in || !d_u || !d_v || !d_o) return FALDOI_ERR_MEM;
@@ -902,3 +915,5 @@ extern "C" int faldoi_bicubic_warp(int device, const float *in, const float *u, 
     FALDOI_CUDA(cudaMemcpy(out, d_o, g.plane * sizeof(float), cudaMemcpyDeviceToHost));
     return FALDOI_OK;
 }
+
+#include "stripes.inc"

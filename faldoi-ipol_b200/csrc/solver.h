@@ -35,6 +35,7 @@ struct faldoi_solver {
 
     // static per-pair planes
     float *I0 = nullptr, *I1 = nullptr, *I1x = nullptr, *I1y = nullptr;
+    size_t i1_plane = 0;  // plane stride of I1/I1x/I1y (== g.plane except in stripe mode, where they are full frames)
     // TV / NLTV state (2 ping-pong sets) and per-warp constants
     float *state = nullptr;
     size_t set_stride = 0;

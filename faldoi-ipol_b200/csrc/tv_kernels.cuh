@@ -34,13 +34,20 @@ struct TvArgs {
     const float *rho_c;    // [B] TVL1 data term constant
     const float *scale;    // [B] CSAD: hypot(Ix^2+Iy^2, 0.01)
     const float *bs;       // [48][B] CSAD: neighbour residuals b_j sorted descending per pixel
-    unsigned *err_max;     // [B][max_iters] float bits of max |du|^2     (DATA_TVL1)
+    unsigned *err_max;     // [B][max_iters] float bits of max |du|^2     (DATA_TVL1), written by this handle
+    const unsigned *err_chk;  // what the exit test reads: err_max, or the max over all stripes of a stripe group
     double *err_sum;       // [B][max_iters] sum of |du|^2                  (DATA_CSAD)
     const int *parity;     // [B]
     Geo g;
     int max_iters;
     float tau, theta, l_t, tol2;
     DivConst dth;  // division by theta
+    // stripe mode (B == 1): neighbours' state arrays, mapped through NVLink peer access.  The rows this
+    // handle owns next to a stripe boundary are ALSO stored into the neighbour's halo row by the
+    // iteration kernel itself (fused compute + halo exchange, no pack/copy/unpack launches).
+    float *peer_up, *peer_dn;          // neighbour's `state` base, or nullptr
+    size_t peer_up_plane, peer_dn_plane, peer_up_set, peer_dn_set;
+    int peer_up_row, peer_dn_row;      // neighbour-local row index of its halo row
 };
 
 // Has pair b already met the reference's exit test `err > tol^2` (false = stop)
@@ -50,7 +57,7 @@ __device__ __forceinline__ bool pair_active(const TvArgs &a, int b, int it) {
     if (it == 0) return true;
     float e;
     if (DATA == DATA_TVL1)
-        e = __uint_as_float(a.err_max[(size_t)b * a.max_iters + it - 1]);
+        e = __uint_as_float(a.err_chk[(size_t)b * a.max_iters + it - 1]);
     else
         e = (float)a.err_sum[(size_t)b * a.max_iters + it - 1] / (float)(a.g.w * a.g.h);
     return e > a.tol2;

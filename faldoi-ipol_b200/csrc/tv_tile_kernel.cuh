@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
     if (!pair_active<DATA>(a, b, it)) return;
 
     const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    const int yo = a.g.y_off, hg = a.g.hg;  // global row = local row + yo (stripe mode), else 0 / h
     const int x0 = blockIdx.x * TT_W, y0 = blockIdx.y * TT_H;
     const int tid = threadIdx.x;
     const int rows = min(TT_H, h - y0);  // interior rows of this tile that exist
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
         const int y = y0 + r, cx = 4 * (q + 1);  // smem column of the quad's first pixel
         const int gx0 = x0 + 4 * q;
         if (gx0 + 3 < 0 || gx0 >= w) continue;
-        const bool ylast = (y == h - 1);
+        const bool ylast = (y + yo == hg - 1);
         const float4 B1 = *reinterpret_cast<const float4 *>(&S.ub[0][r + 1][cx]);
         const float4 B2 = *reinterpret_cast<const float4 *>(&S.ub[1][r + 1][cx]);
         const float b1[5] = {B1.x, B1.y, B1.z, B1.w, S.ub[0][r + 1][cx + 4]};
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
         const int r = t >> 5, q = t & 31;
         if (r >= rows) continue;
         const int y = y0 + r, cx = 4 * (q + 1), gx0 = x0 + 4 * q;
-        if (gx0 >= pitch) continue;
+        if (gx0 >= pitch || y < a.g.own_lo || y >= a.g.own_hi) continue;  // halo rows belong to the neighbour stripe
+        const int gy = y + yo;
         const float4 M11 = *reinterpret_cast<const float4 *>(&S.xi[0][r + 1][cx]);
         const float4 M12 = *reinterpret_cast<const float4 *>(&S.xi[1][r + 1][cx]);
         const float4 M21 = *reinterpret_cast<const float4 *>(&S.xi[2][r + 1][cx]);
@@ -191,8 +193,8 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int gx = gx0 + k;
-            const float d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, y, w, h);
-            const float d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, y, w, h);
+            const float d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, gy, w, hg);
+            const float d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, gy, w, hg);
             float v1, v2;
             if (DATA == DATA_TVL1) {
                 const float grad = ix[k] * ix[k] + iy[k] * iy[k];
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
                 v2 = u2[k];
                 if (gx < w) {
                     const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / cc[k];
-                    const int np = csad_count(gx, y, w, h);
+                    const int np = csad_count(gx, gy, w, hg);
                     const float med = csad_select(a.bs + (size_t)b * plane + (size_t)y * pitch + gx, ks, np, s, l_t, cc[k]);
                     v1 = u1[k] - ix[k] * med / cc[k];
                     v2 = u2[k] - iy[k] * med / cc[k];
@@ -243,6 +245,25 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
         st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
         st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
         st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+        // stripe boundaries: the same values go straight into the neighbour GPU's halo row (peer stores)
+        if (a.peer_up && y == a.g.own_lo) {
+            float *po = a.peer_up + (size_t)(par ^ 1) * a.peer_up_set + (size_t)a.peer_up_row * pitch + gx0;
+            st4(po + ST_U1 * a.peer_up_plane, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st4(po + ST_U2 * a.peer_up_plane, make_float4(o2[0], o2[1], o2[2], o2[3]));
+            st4(po + ST_UB1 * a.peer_up_plane, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+            st4(po + ST_UB2 * a.peer_up_plane, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+        }
+        if (a.peer_dn && y == a.g.own_hi - 1) {
+            float *po = a.peer_dn + (size_t)(par ^ 1) * a.peer_dn_set + (size_t)a.peer_dn_row * pitch + gx0;
+            st4(po + ST_U1 * a.peer_dn_plane, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st4(po + ST_U2 * a.peer_dn_plane, make_float4(o2[0], o2[1], o2[2], o2[3]));
+            st4(po + ST_UB1 * a.peer_dn_plane, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+            st4(po + ST_UB2 * a.peer_dn_plane, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+            st4(po + ST_XI11 * a.peer_dn_plane, M11);
+            st4(po + ST_XI12 * a.peer_dn_plane, M12);
+            st4(po + ST_XI21 * a.peer_dn_plane, M21);
+            st4(po + ST_XI22 * a.peer_dn_plane, M22);
+        }
     }
 
     // ---- convergence measure ----

@@ -90,7 +90,8 @@ __device__ __forceinline__ float bicubic_sample(const float *__restrict__ img, c
 // rho_c (the CSAD constants kernel consumes it).
 // ---------------------------------------------------------------------------
 struct WarpArgs {
-    const float *I0, *I1, *I1x, *I1y;  // static planes [B]
+    const float *I0, *I1, *I1x, *I1y;  // static planes [B]; in stripe mode I1* are FULL frames (any row can be sampled)
+    size_t i1_plane;                   // plane stride of I1, I1x, I1y
     const float *u1, *u2;              // base of the two flow planes (pair stride = plane)
     float *ub1, *ub2;                  // extrapolated flow, set to u
     float *Ix, *Iy, *rho_c, *I1w;      // outputs [B]
@@ -108,13 +109,14 @@ __global__ void __launch_bounds__(256) warp_constants_kernel(WarpArgs a) {
     const size_t so = off + (size_t)a.parity[b] * a.set_stride;
     const int p = y * a.g.pitch + x;
     const float u1 = a.u1[so + p], u2 = a.u2[so + p];
-    const float uu = x + u1, vv = y + u2;
-    const Taps t = make_taps(uu, vv, a.g.w, a.g.h);
+    const float uu = x + u1, vv = (y + a.g.y_off) + u2;
+    const Taps t = make_taps(uu, vv, a.g.w, a.g.hg);
     float iw = 0.f, ix = 0.f, iy = 0.f;
     if (!t.out) {
-        iw = bicubic_sample(a.I1 + off, t, a.g.pitch);
-        ix = bicubic_sample(a.I1x + off, t, a.g.pitch);
-        iy = bicubic_sample(a.I1y + off, t, a.g.pitch);
+        const size_t off1 = (size_t)b * a.i1_plane;
+        iw = bicubic_sample(a.I1 + off1, t, a.g.pitch);
+        ix = bicubic_sample(a.I1x + off1, t, a.g.pitch);
+        iy = bicubic_sample(a.I1y + off1, t, a.g.pitch);
     }
     a.Ix[off + p] = ix;
     a.Iy[off + p] = iy;

@@ -142,6 +142,25 @@ int faldoi_nltvcsad_PD(const float *I0, float *I1, float *a, int pd, float lambd
 int faldoi_guided_tvl2coupled_occ(const float *I0, const float *I1, const float *I_1, float *u1, float *u2,
                                   float *chi, const faldoi_params *p, int nx, int ny, int verbose);
 
+/* ---- row stripes: ONE large frame pair over several GPUs (>= 4K frames) ------------
+ * The frame is cut into `nstripes` contiguous row blocks, stripe k on CUDA device
+ * devices[k] (devices may repeat, e.g. to exercise the path on one GPU).  Every fused
+ * iteration stores the rows next to a stripe boundary directly into the neighbour GPU's
+ * halo rows over NVLink peer mappings; the exit test uses the maximum over the whole
+ * frame, so results (flow, per-warp iteration counts) are identical to the single-GPU
+ * solve.  Implemented for TVL2 (methods 0,1).  The reference has no counterpart: its
+ * tvl2OF (src/global_faldoi.cpp:556) is single-node OpenMP. */
+typedef struct faldoi_stripes faldoi_stripes;
+int faldoi_stripe_rows(int h, int nstripes, int k, int *row0, int *row1); /* rows [row0,row1) owned by stripe k */
+int faldoi_stripes_create(faldoi_stripes **out, int nstripes, const int *devices, int w, int h, int method);
+void faldoi_stripes_destroy(faldoi_stripes *g);
+/* full-frame arrays (host, or device memory reachable from every stripe's GPU): I0, I1 (w*h), u (2*w*h) */
+int faldoi_stripes_upload(faldoi_stripes *g, const float *I0, const float *I1, const float *u);
+int faldoi_stripes_run(faldoi_stripes *g, const faldoi_params *p); /* synchronous: one host thread per stripe */
+int faldoi_stripes_download(faldoi_stripes *g, float *u, faldoi_log *log);
+float faldoi_stripes_last_run_ms(faldoi_stripes *g);
+long long faldoi_stripes_last_launches(faldoi_stripes *g);
+
 /* ---- device-side preprocessing helpers (row "next" of the scope table) ---- */
 /* centered_gradient (src/utils.cpp:367-423) and bicubic_interpolation_warp
  * (src/bicubic_interpolation.c:245-266) on host arrays, computed on the GPU. */
