@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--warps", type=int, default=5)
     ap.add_argument("--glb-iters", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "stripes"],
+                    help="pairs: independent pairs per GPU (default, the driver's line). stripes: ONE frame pair cut into "
+                         "row stripes over --gpus GPUs with halo exchange over NVLink (3840x2160 by default); one host "
+                         "process drives all GPUs (under torchrun rank 0 does, the other ranks exit)")
     return ap.parse_args()
 
 
@@ -175,6 +179,9 @@ def main():
             "data": "synthetic", "config": cfg}
 
     import numpy as np
+
+    if a.mode == "stripes":
+        return main_stripes(a, rank, base)
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
@@ -331,6 +338,61 @@ def main():
     solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def main_stripes(a, rank, base):
+    """BASELINE.json configs[4], second half: 3840x2160 pair, row stripes + per-iteration halo exchange."""
+    import numpy as np
+    import torch
+    if rank != 0:
+        return
+    w, h = (a.width, a.height) if (a.width, a.height) != (1024, 436) else (3840, 2160)
+    npix = w * h
+    fb = importlib.import_module("faldoi-ipol_b200")
+    ng = a.gpus
+    if not torch.cuda.is_available() or torch.cuda.device_count() < ng:
+        raise SystemExit("bench.py --mode stripes --gpus %d: not enough CUDA devices" % ng)
+    d = make_pairs(1, w, h, 2000, torch.device("cuda", 0))
+    host = {k: d[k][0].cpu().pin_memory() for k in ("I0", "I1", "u0")}
+    out = torch.empty(2, h, w).pin_memory()
+    params = fb.default_params(0, 400, a.warps)
+    g = fb.Stripes(w, h, list(range(ng)))
+
+    def step():
+        g.upload_ptrs(host["I0"].data_ptr(), host["I1"].data_ptr(), host["u0"].data_ptr())
+        g.run(params)
+        g.download_ptr(out.data_ptr())
+
+    for _ in range(max(a.warmup, 1)):
+        step()
+    _, log = g.download()
+    iters = sum(log.iters[:a.warps])
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(a.steps):
+        step()
+        dev_ms += g.last_run_ms
+        launches += g.last_launches
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+    units = npix * iters
+    peak, peak_src = peak_hbm()
+    ach = 80 * units * a.steps / (dev_ms / 1e3) / 1e9
+    cfg = dict(base["config"], workload="synthetic %dx%d pair cut into %d row stripes (one per GPU), halo rows exchanged every "
+               "iteration by NVLink peer stores from the iteration kernel; TVL2, %d warps x <=400 iters" % (w, h, ng, a.warps),
+               width=w, height=h, pairs_per_gpu=None, l2_policy="state %.1f GB >> L2" % (23 * npix * 4 / 1e9))
+    line = dict(base, config=cfg, scaling="strong", value=units * a.steps / (dev_ms / 1e3) / 1e6,
+                ms_per_step=dev_ms / a.steps, iters_per_pair=iters, gpu_launches=int(launches),
+                e2e={"value": units * a.steps / t_e2e / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": (ng + 3) * npix * 4,
+                     "d2h_bytes_per_step": 2 * npix * 4},
+                roofline={"bound": "hbm", "kernel": "tv_tile_kernel", "achieved": ach, "peak": peak * ng, "peak_source": peak_src +
+                          " x %d GPUs" % ng, "unit": "GB/s", "frac": ach / (peak * ng), "alg_bytes_per_px_iter": 80, "traffic": None},
+                clocks=clocks)
+    print(json.dumps(line))
+    g.close()
 
 
 if __name__ == "__main__":

@@ -249,6 +249,12 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
         ALLOC(s->occ, (size_t)OCC_PLANES * B * P);
     }
 #undef ALLOC
+    // function attributes are per device: opt the tile kernels into 97 KB of dynamic shared memory here
+    if (!cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)),
+                 "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)),
+                 "cudaFuncSetAttribute"))
+        return fail(FALDOI_ERR_CUDA);
     if (!cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize")) return fail(FALDOI_ERR_CUDA);
     *out = s;
     return FALDOI_OK;
@@ -380,11 +386,6 @@ static bool use_tile_kernel() {
 template <int DATA>
 static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
     if (use_tile_kernel()) {
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[DATA]) {
-            cudaFuncSetAttribute(tv_tile_kernel<DATA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
-            attr_set[DATA] = true;
-        }
         const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
         tv_tile_kernel<DATA><<<grid, 256, sizeof(TileSmem), s->stream>>>(a, it);
         return;
