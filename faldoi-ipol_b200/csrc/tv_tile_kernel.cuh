@@ -133,26 +133,39 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
         float4 X22 = *reinterpret_cast<const float4 *>(&S.xi[3][r + 1][cx]);
         float x11[4] = {X11.x, X11.y, X11.z, X11.w}, x12[4] = {X12.x, X12.y, X12.z, X12.w};
         float x21[4] = {X21.x, X21.y, X21.z, X21.w}, x22[4] = {X22.x, X22.y, X22.z, X22.w};
+        // forward differences of ubar (zero on the last column / row of the FRAME), then
+        // xi <- (xi + tau*grad) / max(1, |xi_old|).  The divisor is exactly 1 wherever |xi_old| <= 1
+        // (x/1 == x), so the IEEE divisions only run for quads that contain a saturated pixel.
+        const bool full = (gx0 + 4 < w);  // all four pixels have a right neighbour inside the frame
+        float nr1[4], nr2[4];
+        float big = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int gx = gx0 + k;
-            const float u1x = (gx < w - 1) ? b1[k + 1] - b1[k] : 0.f;
-            const float u2x = (gx < w - 1) ? b2[k + 1] - b2[k] : 0.f;
+            const float u1x = (full || gx0 + k < w - 1) ? b1[k + 1] - b1[k] : 0.f;
+            const float u2x = (full || gx0 + k < w - 1) ? b2[k + 1] - b2[k] : 0.f;
             const float u1y = ylast ? 0.f : n1[k] - b1[k];
             const float u2y = ylast ? 0.f : n2[k] - b2[k];
             if (DATA == DATA_TVL1) {
-                const float nrm = fmaxf(1.f, sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]));
-                x11[k] = (x11[k] + tau * u1x) / nrm;
-                x12[k] = (x12[k] + tau * u1y) / nrm;
-                x21[k] = (x21[k] + tau * u2x) / nrm;
-                x22[k] = (x22[k] + tau * u2y) / nrm;
+                nr1[k] = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
+                nr2[k] = nr1[k];
             } else {
-                const float m1 = fmaxf(1.f, proj_norm_hypot(x11[k], x12[k]));
-                const float m2 = fmaxf(1.f, proj_norm_hypot(x21[k], x22[k]));
-                x11[k] = (x11[k] + tau * u1x) / m1;
-                x12[k] = (x12[k] + tau * u1y) / m1;
-                x21[k] = (x21[k] + tau * u2x) / m2;
-                x22[k] = (x22[k] + tau * u2y) / m2;
+                nr1[k] = proj_norm_hypot(x11[k], x12[k]);
+                nr2[k] = proj_norm_hypot(x21[k], x22[k]);
+            }
+            big = fmaxf(big, fmaxf(nr1[k], nr2[k]));
+            x11[k] = x11[k] + tau * u1x;
+            x12[k] = x12[k] + tau * u1y;
+            x21[k] = x21[k] + tau * u2x;
+            x22[k] = x22[k] + tau * u2y;
+        }
+        if (big > 1.f) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float d1 = fmaxf(1.f, nr1[k]), d2 = fmaxf(1.f, nr2[k]);
+                x11[k] /= d1;
+                x12[k] /= d1;
+                x21[k] /= d2;
+                x22[k] /= d2;
             }
         }
         *reinterpret_cast<float4 *>(&S.xi[0][r + 1][cx]) = make_float4(x11[0], x11[1], x11[2], x11[3]);
@@ -171,6 +184,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
         const int y = y0 + r, cx = 4 * (q + 1), gx0 = x0 + 4 * q;
         if (gx0 >= pitch || y < a.g.own_lo || y >= a.g.own_hi) continue;  // halo rows belong to the neighbour stripe
         const int gy = y + yo;
+        const bool interior = gx0 > 0 && gx0 + 4 < w && gy > 0 && gy < hg - 1;  // no frame border in this quad
         const float4 M11 = *reinterpret_cast<const float4 *>(&S.xi[0][r + 1][cx]);
         const float4 M12 = *reinterpret_cast<const float4 *>(&S.xi[1][r + 1][cx]);
         const float4 M21 = *reinterpret_cast<const float4 *>(&S.xi[2][r + 1][cx]);
@@ -193,28 +207,28 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int gx = gx0 + k;
-            const float d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, gy, w, hg);
-            const float d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, gy, w, hg);
+            float d1, d2;
+            if (interior) {
+                d1 = (m11[k] - (k ? m11[k - 1] : l11)) + (m12[k] - p12[k]);
+                d2 = (m21[k] - (k ? m21[k - 1] : l21)) + (m22[k] - p22[k]);
+            } else {
+                d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, gy, w, hg);
+                d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, gy, w, hg);
+            }
             float v1, v2;
             if (DATA == DATA_TVL1) {
+                // TH (src/global_faldoi.cpp:693-717) as selects: d = s*(Ix,Iy) with s = +-l_t outside the
+                // band, 0 where the gradient vanishes, -rho/grad inside (the quotient is simply unused
+                // in the other cases)
                 const float grad = ix[k] * ix[k] + iy[k] * iy[k];
                 const float rho = cc[k] + (ix[k] * u1[k] + iy[k] * u2[k]);
-                float e1, e2;
-                if (rho < -l_t * grad) {
-                    e1 = l_t * ix[k];
-                    e2 = l_t * iy[k];
-                } else if (rho > l_t * grad) {
-                    e1 = -l_t * ix[k];
-                    e2 = -l_t * iy[k];
-                } else if (grad_is_zero(grad)) {
-                    e1 = e2 = 0.f;
-                } else {
-                    const float fi = -rho / grad;
-                    e1 = fi * ix[k];
-                    e2 = fi * iy[k];
-                }
-                v1 = u1[k] + e1;
-                v2 = u2[k] + e2;
+                const float thr = l_t * grad;
+                float sc = -rho / grad;
+                sc = grad_is_zero(grad) ? 0.f : sc;
+                sc = (rho > thr) ? -l_t : sc;
+                sc = (rho < -l_t * grad) ? l_t : sc;
+                v1 = u1[k] + sc * ix[k];
+                v2 = u2[k] + sc * iy[k];
             } else {
                 v1 = u1[k];
                 v2 = u2[k];
