@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfaldoi_gpu.so")
+LIB_PATH = os.environ.get("FALDOI_GPU_LIB", os.path.join(HERE, "libfaldoi_gpu.so"))  # override only for kernel-variant experiments
 MAX_WARPS = 64
 
 M_TVL1, M_TVL1_W, M_NLTVL1, M_NLTVL1_W, M_TVCSAD, M_TVCSAD_W, M_NLTVCSAD, M_NLTVCSAD_W, M_TVL1_OCC = range(9)

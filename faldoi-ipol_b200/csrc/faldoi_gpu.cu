@@ -387,7 +387,7 @@ template <int DATA>
 static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
     if (use_tile_kernel()) {
         const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
-        tv_tile_kernel<DATA><<<grid, 256, sizeof(TileSmem), s->stream>>>(a, it);
+        tv_tile_kernel<DATA><<<grid, TT_THREADS, sizeof(TileSmem), s->stream>>>(a, it);
         return;
     }
     const dim3 block(32, 8);

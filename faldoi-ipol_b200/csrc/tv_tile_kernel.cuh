@@ -1,14 +1,16 @@
 // Shared-memory tiled version of the fused TV iteration (same math and interface as
 // tv_iter_kernel in tv_kernels.cuh; see there for the reference citations).
 //
-// One CTA = one 128 x 16 pixel tile of one pair.  All 11 input planes of the tile are
-// staged into shared memory with the bulk async-copy engine (cp.async.bulk ->
-// UBLKCP, one 16-byte-aligned row segment per copy, completion on an mbarrier), so no
-// registers are held while HBM latency is outstanding and two CTAs per SM overlap one
-// tile's loads with the other's arithmetic:
-//   ubar1,ubar2     rows y0-1 .. y0+16, cols x0-4 .. x0+131   (forward differences + halo)
-//   xi11..xi22      rows y0-1 .. y0+15, cols x0-4 .. x0+131   (old duals incl. top/left halo)
-//   u1,u2,c0,Ix,Iy  rows y0   .. y0+15, cols x0   .. x0+127   (c0 = rho_c or the CSAD scale)
+// One CTA = one 128 x TT_H pixel tile of one pair (TT_H = 8: 51 KB of shared memory, 256 threads,
+// 64 registers -> 4 CTAs = 32 warps per SM; measured on B200: 128x16 tiles at 2 CTAs/SM reach 0.61 of
+// the HBM roofline, 128x8 at 4 CTAs/SM 0.71-0.76, see profiles/README.md).  All 11 input planes of
+// the tile are staged into shared memory with the bulk async-copy engine (cp.async.bulk ->
+// UBLKCP, one 16-byte-aligned row segment per copy, completion on an mbarrier), so no registers are
+// held while HBM latency is outstanding and the CTAs of an SM overlap one tile's loads with the
+// others' arithmetic:
+//   ubar1,ubar2     rows y0-1 .. y0+TT_H,   cols x0-4 .. x0+131   (forward differences + halo)
+//   xi11..xi22      rows y0-1 .. y0+TT_H-1, cols x0-4 .. x0+131   (old duals incl. top/left halo)
+//   u1,u2,c0,Ix,Iy  rows y0   .. y0+TT_H-1, cols x0   .. x0+127   (c0 = rho_c or the CSAD scale)
 // phase 1: xi_new on the tile plus its top row and left column, in place in smem
 // phase 2: divergence from smem, data term, primal step, extrapolation, error; the 8 output
 //          planes go straight to HBM as float4.
@@ -21,14 +23,20 @@
 
 namespace faldoi {
 
-enum { TT_W = 128, TT_H = 16, TT_PW = TT_W + 8 };  // tile size, padded smem row (cols x0-4 .. x0+131)
+#ifndef FALDOI_TT_H
+#define FALDOI_TT_H 8
+#endif
+#ifndef FALDOI_TT_CTAS
+#define FALDOI_TT_CTAS 4
+#endif
+enum { TT_W = 128, TT_H = FALDOI_TT_H, TT_PW = TT_W + 8, TT_THREADS = 32 * TT_H };  // one phase-2 quad per thread  // tile size, padded smem row (cols x0-4 .. x0+131)
 
 struct TileSmem {
     float ub[2][TT_H + 2][TT_PW];  // rows y0-1 .. y0+16
     float xi[4][TT_H + 1][TT_PW];  // rows y0-1 .. y0+15
     float pl[5][TT_H][TT_W];       // u1, u2, c0, Ix, Iy
-    float red[8];
-    double redd[8];
+    float red[TT_THREADS / 32];
+    double redd[TT_THREADS / 32];
     unsigned long long bar;
 };
 
@@ -42,7 +50,7 @@ __device__ __forceinline__ void bulk_row(void *dst_smem, const float *src, unsig
 }
 
 template <int DATA>
-__global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
+__global__ void __launch_bounds__(TT_THREADS, FALDOI_TT_CTAS) tv_tile_kernel(TvArgs a, int it) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
     const int b = blockIdx.z;
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
     __syncthreads();
     {
         // job list: [0, 2*18) ubar rows, [36, 36+4*17) xi rows, [104, 104+5*16) plain rows
-        for (int j = tid; j < 2 * (TT_H + 2) + 4 * (TT_H + 1) + 5 * TT_H; j += 256) {
+        for (int j = tid; j < 2 * (TT_H + 2) + 4 * (TT_H + 1) + 5 * TT_H; j += TT_THREADS) {
             if (j < 2 * (TT_H + 2)) {
                 const int k = j / (TT_H + 2), r = j % (TT_H + 2) - 1;
                 if (r >= ub_lo && r <= ub_hi)
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
     const float tau = a.tau, l_t = a.l_t;
 
     // ---- phase 1: dual step on rows -1..rows-1 (relative), column quads -1..31 (quad -1 = cols x0-4..x0-1) ----
-    for (int t = tid; t < (TT_H + 1) * 33; t += 256) {
+    for (int t = tid; t < (TT_H + 1) * 33; t += TT_THREADS) {
         const int r = t / 33 - 1, q = t % 33 - 1;
         if (r < xi_lo || r > xi_hi) continue;
         const int y = y0 + r, cx = 4 * (q + 1);  // smem column of the quad's first pixel
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
     // ---- phase 2: divergence, data term, primal step, extrapolation ----
     float emax = 0.f;
     double esum = 0.0;
-    for (int t = tid; t < TT_H * 32; t += 256) {
+    for (int t = tid; t < TT_H * 32; t += TT_THREADS) {
         const int r = t >> 5, q = t & 31;
         if (r >= rows) continue;
         const int y = y0 + r, cx = 4 * (q + 1), gx0 = x0 + 4 * q;
@@ -293,11 +301,11 @@ __global__ void __launch_bounds__(256, 2) tv_tile_kernel(TvArgs a, int it) {
     if (tid == 0) {
         if (DATA == DATA_TVL1) {
             float m = S.red[0];
-            for (int i = 1; i < 8; i++) m = fmaxf(m, S.red[i]);
+            for (int i = 1; i < TT_THREADS / 32; i++) m = fmaxf(m, S.red[i]);
             atomicMax(a.err_max + (size_t)b * a.max_iters + it, __float_as_uint(m));
         } else {
             double t = S.redd[0];
-            for (int i = 1; i < 8; i++) t += S.redd[i];
+            for (int i = 1; i < TT_THREADS / 32; i++) t += S.redd[i];
             atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
         }
     }
