@@ -223,6 +223,11 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
     s->log_err = s->dmalloc(B * FALDOI_MAX_WARPS);
     if (!s->parity || !s->log_iters || !s->log_err) return fail(FALDOI_ERR_MEM);
     if (s->alloc_err(400) != FALDOI_OK) return fail(FALDOI_ERR_MEM);
+    s->d_active = (int *)s->dmalloc(4);
+    if (!s->d_active || !cuda_ok(cudaHostAlloc((void **)&s->h_active, 4 * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"))
+        return fail(FALDOI_ERR_MEM);
+    for (int k = 0; k < 4; k++)
+        if (!cuda_ok(cudaEventCreateWithFlags(&s->chunk_ev[k], cudaEventDisableTiming), "cudaEventCreate")) return fail(FALDOI_ERR_CUDA);
 
     const Family fam = method_family(method);
     if (fam == FAM_TV || fam == FAM_NLTV) {
@@ -266,6 +271,9 @@ extern "C" void faldoi_solver_destroy(faldoi_solver *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (void *p : s->allocs) cudaFree(p);
     for (cudaEvent_t e : s->phase_ev) cudaEventDestroy(e);
+    for (int k = 0; k < 4; k++)
+        if (s->chunk_ev[k]) cudaEventDestroy(s->chunk_ev[k]);
+    if (s->h_active) cudaFreeHost(s->h_active);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -333,6 +341,17 @@ __global__ void finalize_warp_kernel(const unsigned *err_max, const double *err_
     if (parity) parity[b] = (parity[b] + n) & 1;
     log_iters[b * FALDOI_MAX_WARPS + warp_idx] = n;
     log_err[b * FALDOI_MAX_WARPS + warp_idx] = e;
+}
+
+// number of pairs whose exit test still holds after iteration `it` (see pair_active)
+__global__ void count_active_kernel(const unsigned *err_max, const double *err_sum, int use_sum, int npairs, int max_iters,
+                                    int it, float tol2, float npix, int *out) {
+    int n = 0;
+    for (int b = 0; b < npairs; b++) {
+        const float e = use_sum ? (float)err_sum[(size_t)b * max_iters + it] / npix : __uint_as_float(err_max[(size_t)b * max_iters + it]);
+        n += (e > tol2);
+    }
+    *out = n;
 }
 
 __global__ void export_flow_kernel(const float *state, size_t set_stride, const int *parity, float *packed, Geo g) {
@@ -482,14 +501,31 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
-        for (int it = 0; it < p->max_iters; it++) {
-            if (csad)
-                launch_tv_iter<DATA_CSAD>(s, a, it, npairs, R);
-            else
-                launch_tv_iter<DATA_TVL1>(s, a, it, npairs, R);
+        // All launches of a warp are enqueued without waiting for results; converged pairs return at
+        // once.  To stop enqueuing once EVERY pair has met the exit test, the active-pair count is
+        // copied to pinned memory every CHUNK launches and inspected two chunks later (so the GPU
+        // always has at least one full chunk queued and never waits for the host).
+        const int CHUNK = 25;
+        for (int c = 0, it = 0; it < p->max_iters; c++) {
+            if (c >= 2) {
+                FALDOI_CUDA(cudaEventSynchronize(s->chunk_ev[(c - 2) & 3]));
+                if (s->h_active[(c - 2) & 3] == 0) break;
+            }
+            const int end = (it + CHUNK < p->max_iters) ? it + CHUNK : p->max_iters;
+            for (; it < end; it++) {
+                if (csad)
+                    launch_tv_iter<DATA_CSAD>(s, a, it, npairs, R);
+                else
+                    launch_tv_iter<DATA_TVL1>(s, a, it, npairs, R);
+                s->launches++;
+            }
+            count_active_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, npairs, p->max_iters, it - 1, a.tol2,
+                                                        (float)(g.w * g.h), s->d_active + (c & 3));
+            FALDOI_CUDA(cudaMemcpyAsync(s->h_active + (c & 3), s->d_active + (c & 3), sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            FALDOI_CUDA(cudaEventRecord(s->chunk_ev[c & 3], s->stream));
+            s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
-        s->launches += p->max_iters;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, 0, s->parity,
                                                                        s->log_iters, s->log_err, p->max_iters, a.tol2,
                                                                        (float)(g.w * g.h), wp, npairs);

@@ -14,6 +14,16 @@ namespace faldoi {
 
 enum { NL_SLOTS = 24 };
 
+// The NLTV models are held to the north star's fp32 tolerance, not to bit equality (their
+// weights already differ from glibc's expf in the last bit), so the 192 divisions per pixel
+// and iteration of the dual updates use the 2-ulp approximate division (MUFU.RCP + FMUL).
+// Build with -DFALDOI_NLTV_IEEE_DIV for IEEE division.
+#ifdef FALDOI_NLTV_IEEE_DIV
+#define NL_DIV(a, b) ((a) / (b))
+#else
+#define NL_DIV(a, b) __fdividef((a), (b))
+#endif
+
 struct NlOffsets {
     float ws[NL_SLOTS];  // exp(-hypot(l,k)/2) per slot, evaluated on the host with libm (get_wspatial_2 :943-952)
 };
@@ -156,18 +166,18 @@ __global__ void __launch_bounds__(256) nltv_iter_kernel(NlArgs a, int it, int ba
                 const float q1 = sin[ST_UB1 * ks + q], q2 = sin[ST_UB2 * ks + q];
                 const float wtq = a.wt[off + q];
                 // own dual, slot s
-                const float g1 = wv * (c1 - q1) / wtp;
-                const float Pn = (din[(size_t)s * ks + p] + tau * g1) / (1 + tau * fabsf(g1));
-                const float g2 = wv * (c2 - q2) / wtp;
-                const float Qn = (din[(size_t)(NL_SLOTS + s) * ks + p] + tau * g2) / (1 + tau * fabsf(g2));
+                const float g1 = NL_DIV(wv * (c1 - q1), wtp);
+                const float Pn = NL_DIV(din[(size_t)s * ks + p] + tau * g1, 1 + tau * fabsf(g1));
+                const float g2 = NL_DIV(wv * (c2 - q2), wtp);
+                const float Qn = NL_DIV(din[(size_t)(NL_SLOTS + s) * ks + p] + tau * g2, 1 + tau * fabsf(g2));
                 dout[(size_t)s * ks + p] = Pn;
                 dout[(size_t)(NL_SLOTS + s) * ks + p] = Qn;
                 // neighbour's reciprocal dual, slot 23-s at q
                 const int rs = NL_SLOTS - 1 - s;
-                const float h1 = wv * (q1 - c1) / wtq;
-                const float Pr = (din[(size_t)rs * ks + q] + tau * h1) / (1 + tau * fabsf(h1));
-                const float h2 = wv * (q2 - c2) / wtq;
-                const float Qr = (din[(size_t)(NL_SLOTS + rs) * ks + q] + tau * h2) / (1 + tau * fabsf(h2));
+                const float h1 = NL_DIV(wv * (q1 - c1), wtq);
+                const float Pr = NL_DIV(din[(size_t)rs * ks + q] + tau * h1, 1 + tau * fabsf(h1));
+                const float h2 = NL_DIV(wv * (q2 - c2), wtq);
+                const float Qr = NL_DIV(din[(size_t)(NL_SLOTS + rs) * ks + q] + tau * h2, 1 + tau * fabsf(h2));
                 dP += wv * (Pn - Pr);
                 dQ += wv * (Qn - Qr);
             }

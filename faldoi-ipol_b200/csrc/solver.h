@@ -60,6 +60,11 @@ struct faldoi_solver {
     bool dc_valid = false;
     int *dc_flag = nullptr;
 
+    // early termination: every CHUNK launches a 1-thread kernel counts the pairs still iterating;
+    // the host looks at the count two chunks behind the one it is enqueuing
+    int *d_active = nullptr, *h_active = nullptr;  // [4] device / pinned host
+    cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
     float last_ms = 0.f;
     float last_iter_ms = 0.f;             // time inside the per-iteration launches only
     std::vector<cudaEvent_t> phase_ev;    // pairs (begin,end) around each warp's iteration loop

@@ -67,7 +67,7 @@ def test_batch_equals_single(fb, po):
         assert np.array_equal(u, ou)
         iters_seen.add(tuple(oits))
     assert len(iters_seen) > 1, "test needs pairs with different exit iterations"
-    assert s.last_launches > 3 * 400
+    assert s.last_launches > 3 * 50  # iteration launches really ran (early termination stops enqueuing once all pairs exit)
     s.close()
 
 
