@@ -239,6 +239,8 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
             ALLOC(s->scale, B * P);
             ALLOC(s->I1w, B * P);
             ALLOC(s->bs, 48 * B * P);
+            s->csad_hint = (unsigned char *)s->dmalloc((B * P + 3) / 4);
+            if (!s->csad_hint) return fail(FALDOI_ERR_MEM);
         } else {
             ALLOC(s->rho_c, B * P);
         }
@@ -446,6 +448,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.rho_c = s->rho_c;
     a.scale = s->scale;
     a.bs = s->bs;
+    a.csad_hint = s->csad_hint;
     a.err_max = s->err_max;
     a.err_chk = s->err_max;
     a.err_sum = s->err_sum;
@@ -498,6 +501,8 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             ca.hyp = 1;
             const dim3 cb(32, 4);
             csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
+            // the residuals were re-sorted: restart the rank hints from the middle (24 of 48)
+            FALDOI_CUDA(cudaMemsetAsync(s->csad_hint, 24, (size_t)g.B * g.plane, s->stream));
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
@@ -569,6 +574,7 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.rho_c = s->rho_c;
     a.scale = s->scale;
     a.bs = s->bs;
+    a.csad_hint = s->csad_hint;
     a.err_sum = s->err_sum;
     a.g = g;
     a.max_iters = p->max_iters;
@@ -615,6 +621,8 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             ca.hyp = 0;
             const dim3 cb(32, 4);
             csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
+            // the residuals were re-sorted: restart the rank hints from the middle (24 of 48)
+            FALDOI_CUDA(cudaMemsetAsync(s->csad_hint, 24, (size_t)g.B * g.plane, s->stream));
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;

@@ -40,6 +40,7 @@ struct faldoi_solver {
     float *state = nullptr;
     size_t set_stride = 0;
     float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr, *bs = nullptr;
+    unsigned char *csad_hint = nullptr;  // [B][plane] bytes
     // NLTV: Lab, weights, duals
     float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *dual = nullptr;
     size_t dual_set_stride = 0;

@@ -33,7 +33,9 @@ struct TvArgs {
     const float *Ix, *Iy;  // [B] warped gradient of I1
     const float *rho_c;    // [B] TVL1 data term constant
     const float *scale;    // [B] CSAD: hypot(Ix^2+Iy^2, 0.01)
-    const float *bs;       // [48][B] CSAD: neighbour residuals b_j sorted descending per pixel
+    const float *bs;       // [B][plane][48] CSAD: per pixel, its neighbour residuals b_j sorted descending (one 192-byte
+                           // record per pixel, so the two probes of a warm-started search share a 32-byte sector)
+    unsigned char *csad_hint;  // [B] bytes per pixel: last iteration's rank m* (see csad_select)
     unsigned *err_max;     // [B][max_iters] float bits of max |du|^2     (DATA_TVL1), written by this handle
     const unsigned *err_chk;  // what the exit test reads: err_max, or the max over all stripes of a stripe group
     double *err_sum;       // [B][max_iters] sum of |du|^2                  (DATA_CSAD)
@@ -68,24 +70,60 @@ __device__ __forceinline__ bool pair_active(const TvArgs &a, int b, int it) {
 // With a_m = -(bs_m - s) ascending (bs sorted descending) and the thresholds
 // t_m descending, that element equals min_m max(a_m, t_m), m = 0..n-1, found
 // by bisection on the monotone predicate a_m >= t_m  ("CSAD rank").
-__device__ __forceinline__ float csad_select(const float *__restrict__ bs, size_t stride, int np, float s,
-                                             float l_t, float scale) {
+struct CsadProbe {
+    int c;         // rank tried first: last iteration's m*
+    float bc, bl;  // sorted residuals at ranks c and c-1 (raw, before the shift by s)
+};
+
+// Issue the two probe loads of the warm-started search early (they do not depend on the
+// current flow), so their HBM latency overlaps other work of the kernel.
+__device__ __forceinline__ CsadProbe csad_probe(const float *__restrict__ bs, int np, unsigned char hint) {
+    CsadProbe pr;
+    pr.c = min((int)hint, np);
+    pr.bc = (pr.c < np) ? __ldg(bs + pr.c) : 0.f;
+    pr.bl = (pr.c > 0) ? __ldg(bs + pr.c - 1) : 0.f;
+    return pr;
+}
+
+__device__ __forceinline__ float csad_select(const float *__restrict__ bs, int np, float s, float l_t, float scale,
+                                             const CsadProbe &pr, unsigned char *hint_out) {
+    // m* = first m in [0, np) with a_m >= t_m (np if none); the answer is min(a_{m*}, t_{m*-1}).
+    // m* moves slowly from one iteration to the next (s changes little), so last iteration's m*
+    // is tried first with two independent probes; only if it moved is the bisection run on the
+    // side the probes point to.  Any route finds the same m*, hence the same value.
+    auto a_at = [&](int m) { return -(__ldg(bs + m) - s); };  // bs: this pixel's 48 sorted residuals (192 contiguous bytes)
+    auto t_at = [&](int m) { return (float)(np - 2 * m) * l_t * scale; };
     int lo = 0, hi = np;
-    float a_lo = 0.f;  // a(lo) when lo < np is the final answer candidate
+    float a_hi = 0.f;  // a(hi) whenever hi < np
+    const int c = pr.c;
+    {
+        const float ac = -(pr.bc - s), al = -(pr.bl - s);
+        const bool pc = (c == np) || (ac >= t_at(c));    // predicate holds at c
+        const bool pl = (c > 0) && (al >= t_at(c - 1));  // predicate holds at c-1
+        if (pc && !pl) {
+            lo = hi = c;
+            a_hi = ac;
+        } else if (pl) {  // m* <= c-1
+            hi = c - 1;
+            a_hi = al;
+        } else {  // predicate false at c: m* > c
+            lo = c + 1;
+        }
+    }
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const float am = -(__ldg(bs + (size_t)mid * stride) - s);
-        const float tm = (float)(np - 2 * mid) * l_t * scale;
-        if (am >= tm) {
+        const float am = a_at(mid);
+        if (am >= t_at(mid)) {
             hi = mid;
-            a_lo = am;
+            a_hi = am;
         } else {
             lo = mid + 1;
         }
     }
+    *hint_out = (unsigned char)lo;
     float ans = INFINITY;
-    if (lo < np) ans = a_lo;  // a(lo): lo == last hi for which the predicate held
-    if (lo > 0) ans = fminf(ans, (float)(np - 2 * (lo - 1)) * l_t * scale);
+    if (lo < np) ans = a_hi;
+    if (lo > 0) ans = fminf(ans, t_at(lo - 1));
     return ans;
 }
 
@@ -300,7 +338,9 @@ __global__ void __launch_bounds__(256, 2) tv_iter_kernel(TvArgs a, int it) {
                 if (gx < w) {
                     const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / sc[k];
                     const int np = csad_count(gx, y, w, h);
-                    const float med = csad_select(a.bs + (size_t)b * plane + (size_t)y * pitch + gx, ks, np, s, l_t, sc[k]);
+                    const size_t pp = (size_t)b * plane + (size_t)y * pitch + gx;
+                    const CsadProbe pr = csad_probe(a.bs + pp * 48, np, a.csad_hint[pp]);
+                    const float med = csad_select(a.bs + pp * 48, np, s, l_t, sc[k], pr, a.csad_hint + pp);
                     v1 = u1[k] - ix[k] * med / sc[k];
                     v2 = u2[k] - iy[k] * med / sc[k];
                 }
@@ -366,7 +406,7 @@ __global__ void __launch_bounds__(256, 2) tv_iter_kernel(TvArgs a, int it) {
 // CSAD per-warp constants (src/global_faldoi.cpp:1514-1534): scale =
 // hypot(Ix^2+Iy^2, 0.01) and, for the in-image neighbours j of the 7x7 window,
 //   b_j = (I0[p] - I0[j] - I1w[p] + I1w[j] + Ix*u1 + Iy*u2) / scale
-// stored SORTED DESCENDING per pixel (48 planes) so the per-iteration rank
+// stored SORTED DESCENDING per pixel (a 48-float record) so the per-iteration rank
 // selection is a bisection instead of the reference's std::sort of 97 floats.
 // hyp = 0 is the NLTV-CSAD variant (:1698-1723): scale = sqrt(Ix^2+Iy^2),
 // only where Ix^2+Iy^2 > 1e-8 (elsewhere scale := 0 marks "v = u").
@@ -377,7 +417,7 @@ struct CsadArgs {
     const int *parity;
     size_t set_stride;
     float *scale;  // [B]
-    float *bs;     // [48][B]
+    float *bs;     // [B][plane][48]
     Geo g;
     int hyp;
 };
@@ -425,13 +465,12 @@ __global__ void __launch_bounds__(128) csad_constants_kernel(CsadArgs a) {
             bv[s++] = v;
         }
     // rank sort (descending, ties by slot) -- 48x48 compares, all in registers
-    const size_t ks = (size_t)a.g.B * a.g.plane;
 #pragma unroll
     for (int i = 0; i < 48; i++) {
         int rank = 0;
 #pragma unroll
         for (int j = 0; j < 48; j++) rank += (bv[j] > bv[i]) || (bv[j] == bv[i] && j < i);
-        a.bs[(size_t)rank * ks + off + p] = bv[i];
+        a.bs[(off + p) * 48 + rank] = bv[i];
     }
 }
 

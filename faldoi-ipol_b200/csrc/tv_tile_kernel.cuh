@@ -26,6 +26,9 @@ namespace faldoi {
 #ifndef FALDOI_TT_H
 #define FALDOI_TT_H 8
 #endif
+#ifndef FALDOI_TT_CTAS_CSAD
+#define FALDOI_TT_CTAS_CSAD 3
+#endif
 #ifndef FALDOI_TT_CTAS
 #define FALDOI_TT_CTAS 4
 #endif
@@ -50,7 +53,7 @@ __device__ __forceinline__ void bulk_row(void *dst_smem, const float *src, unsig
 }
 
 template <int DATA>
-__global__ void __launch_bounds__(TT_THREADS, FALDOI_TT_CTAS) tv_tile_kernel(TvArgs a, int it) {
+__global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS_CSAD : FALDOI_TT_CTAS) tv_tile_kernel(TvArgs a, int it) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
     const int b = blockIdx.z;
@@ -68,6 +71,27 @@ __global__ void __launch_bounds__(TT_THREADS, FALDOI_TT_CTAS) tv_tile_kernel(TvA
     float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
     const float *c0 = (DATA == DATA_TVL1 ? a.rho_c : a.scale) + (size_t)b * plane;
     const float *cIx = a.Ix + (size_t)b * plane, *cIy = a.Iy + (size_t)b * plane;
+
+    // CSAD: this thread's phase-2 quad is known now; fetch its four rank hints (one 4-byte load) and
+    // the two probe values per pixel before anything else, so their latency hides behind the
+    // staging wait and phase 1.
+    CsadProbe probe[4];
+    unsigned char *hint_ptr = nullptr;
+    bool csad_task = false;
+    if (DATA == DATA_CSAD) {
+        const int r = tid >> 5, q = tid & 31;
+        const int y = y0 + r, gx0 = x0 + 4 * q;
+        csad_task = (r < rows && gx0 < w && y >= a.g.own_lo && y < a.g.own_hi);
+        if (csad_task) {
+            const size_t pp = (size_t)b * plane + (size_t)y * pitch + gx0;
+            hint_ptr = a.csad_hint + pp;
+            const uchar4 h4 = *reinterpret_cast<const uchar4 *>(hint_ptr);
+            const unsigned char hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (gx0 + k < w) probe[k] = csad_probe(a.bs + (pp + k) * 48, csad_count(gx0 + k, y + yo, w, hg), hh[k]);
+        }
+    }
 
     // ---- stage the tile: thread 0 arms the barrier, then one row segment per thread ----
     const int ub_lo = (y0 > 0) ? -1 : 0, ub_hi = min(TT_H, h - 1 - y0);  // ubar rows (relative) lo..hi inclusive
@@ -243,7 +267,8 @@ __global__ void __launch_bounds__(TT_THREADS, FALDOI_TT_CTAS) tv_tile_kernel(TvA
                 if (gx < w) {
                     const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / cc[k];
                     const int np = csad_count(gx, gy, w, hg);
-                    const float med = csad_select(a.bs + (size_t)b * plane + (size_t)y * pitch + gx, ks, np, s, l_t, cc[k]);
+                    const float med = csad_select(a.bs + ((size_t)b * plane + (size_t)y * pitch + gx) * 48, np, s, l_t, cc[k], probe[k],
+                                                  hint_ptr + k);
                     v1 = u1[k] - ix[k] * med / cc[k];
                     v2 = u2[k] - iy[k] * med / cc[k];
                 }
