@@ -125,8 +125,10 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
             }
         }
     }
-    // wait for the bytes (phase 0)
-    {
+    // wait for the bytes (phase 0): one thread polls the mbarrier, the other warps sleep on the CTA
+    // barrier instead of burning issue slots in a spin loop (the acquire of the poller is carried
+    // to them by bar.sync)
+    if (tid == 0) {
         unsigned done = 0;
         while (!done) {
             asm volatile(
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
                 : "memory");
         }
     }
+    __syncthreads();
 
     const float tau = a.tau, l_t = a.l_t;
 
