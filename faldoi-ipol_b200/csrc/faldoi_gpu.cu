@@ -161,6 +161,52 @@ int faldoi_solver::alloc_err(int max_iters) {
     return FALDOI_OK;
 }
 
+// ---------------------------------------------------------------------------
+// TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_plane_map(CUtensorMap *out, float *base, const Geo &g, size_t nplanes, int box_w, int box_h) {
+    static EncodeTiledFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeTiledFn)fn;
+    }();
+    if (!encode) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return FALDOI_ERR_CUDA;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.h, (cuuint64_t)nplanes};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * sizeof(float), (cuuint64_t)g.plane * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return FALDOI_ERR_CUDA;
+    }
+    return FALDOI_OK;
+}
+
+static int make_tile_maps(faldoi_solver *s) {
+    const Geo &g = s->g;
+    const size_t nstate = (size_t)2 * ST_COUNT * g.B;
+    float *c0 = method_is_csad(s->method) ? s->scale : s->rho_c;
+    int rc;
+    if ((rc = make_plane_map(&s->maps.ub, s->state, g, nstate, TT_PW, TT_UB_ROWS))) return rc;
+    if ((rc = make_plane_map(&s->maps.xi, s->state, g, nstate, TT_PW, TT_XI_ROWS))) return rc;
+    if ((rc = make_plane_map(&s->maps.pl, s->state, g, nstate, TT_W, TT_H))) return rc;
+    if ((rc = make_plane_map(&s->maps.c0, c0, g, g.B, TT_W, TT_H))) return rc;
+    if ((rc = make_plane_map(&s->maps.ix, s->Ix, g, g.B, TT_W, TT_H))) return rc;
+    if ((rc = make_plane_map(&s->maps.iy, s->Iy, g, g.B, TT_W, TT_H))) return rc;
+    return FALDOI_OK;
+}
+
 struct StripeGeo {
     int y_off, hg, own_lo, own_hi;
 };
@@ -245,6 +291,7 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
             ALLOC(s->rho_c, B * P);
         }
     }
+    if (fam == FAM_TV && make_tile_maps(s) != FALDOI_OK) return fail(FALDOI_ERR_CUDA);
     if (fam == FAM_NLTV) {
         ALLOC(s->lab, 3 * B * P);
         ALLOC(s->wgt, (size_t)NL_SLOTS * B * P);
@@ -257,9 +304,9 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
     }
 #undef ALLOC
     // function attributes are per device: opt the tile kernels into 97 KB of dynamic shared memory here
-    if (!cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)),
+    if (!cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
                  "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)),
+        !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
                  "cudaFuncSetAttribute"))
         return fail(FALDOI_ERR_CUDA);
     if (!cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize")) return fail(FALDOI_ERR_CUDA);
@@ -408,7 +455,7 @@ template <int DATA>
 static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
     if (use_tile_kernel()) {
         const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
-        tv_tile_kernel<DATA><<<grid, TT_THREADS, sizeof(TileSmem), s->stream>>>(a, it);
+        tv_tile_kernel<DATA><<<grid, TT_THREADS, sizeof(TileSmem) + 128, s->stream>>>(s->maps, a, it);
         return;
     }
     const dim3 block(32, 8);

@@ -7,6 +7,7 @@
 
 #include "../../include/faldoi_gpu.h"
 #include "common.cuh"
+#include "tv_tile_kernel.cuh"
 
 namespace faldoi {
 
@@ -41,6 +42,7 @@ struct faldoi_solver {
     size_t set_stride = 0;
     float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr, *bs = nullptr;
     unsigned char *csad_hint = nullptr;  // [B][plane] bytes
+    faldoi::TileMaps maps{};             // TMA descriptors of the tile kernel (TV family)
     // NLTV: Lab, weights, duals
     float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *dual = nullptr;
     size_t dual_set_stride = 0;

@@ -18,6 +18,8 @@
 // copies that would fall outside the plane are skipped (rows) or land in the allocation's
 // guard bands (columns), see faldoi_solver_create.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "tv_kernels.cuh"
 
@@ -34,28 +36,51 @@ namespace faldoi {
 #endif
 enum { TT_W = 128, TT_H = FALDOI_TT_H, TT_PW = TT_W + 8, TT_THREADS = 32 * TT_H };  // one phase-2 quad per thread  // tile size, padded smem row (cols x0-4 .. x0+131)
 
+// Shared-memory planes are TMA box destinations: dense [rows][TT_PW] (or [TT_H][TT_W]), each
+// plane padded to a multiple of 128 bytes so every box lands on a 128-byte boundary.
+enum {
+    TT_UB_ROWS = TT_H + 2,
+    TT_XI_ROWS = TT_H + 1,
+    TT_UB_FLOATS = (TT_UB_ROWS * TT_PW + 31) / 32 * 32,
+    TT_XI_FLOATS = (TT_XI_ROWS * TT_PW + 31) / 32 * 32,
+    TT_PL_FLOATS = TT_H * TT_W,
+    TT_TX_BYTES = (2 * TT_UB_ROWS * TT_PW + 4 * TT_XI_ROWS * TT_PW + 5 * TT_H * TT_W) * 4
+};
+
 struct TileSmem {
-    float ub[2][TT_H + 2][TT_PW];  // rows y0-1 .. y0+16
-    float xi[4][TT_H + 1][TT_PW];  // rows y0-1 .. y0+15
-    float pl[5][TT_H][TT_W];       // u1, u2, c0, Ix, Iy
+    float ub_[2][TT_UB_FLOATS];  // rows y0-1 .. y0+TT_H,   cols x0-4 .. x0+131
+    float xi_[4][TT_XI_FLOATS];  // rows y0-1 .. y0+TT_H-1, cols x0-4 .. x0+131
+    float pl_[5][TT_PL_FLOATS];  // u1, u2, c0, Ix, Iy: rows y0 .. y0+TT_H-1, cols x0 .. x0+127
     float red[TT_THREADS / 32];
     double redd[TT_THREADS / 32];
     unsigned long long bar;
+    __device__ __forceinline__ float *ub(int k, int row) { return &ub_[k][row * TT_PW]; }
+    __device__ __forceinline__ float *xi(int k, int row) { return &xi_[k][row * TT_PW]; }
+    __device__ __forceinline__ float *pl(int k, int row) { return &pl_[k][row * TT_W]; }
+};
+
+// One tensor map per (array, box shape).  All are 3-D {x = pitch, y = rows, z = plane index};
+// out-of-range rows / columns of a box are zero-filled by the TMA unit, which is all the frame
+// borders need (the boundary-aware stencils never use those values).
+struct TileMaps {
+    CUtensorMap ub, xi, pl;  // the state array [2 sets][ST_COUNT][B]: boxes 136x(H+2), 136x(H+1), 128xH
+    CUtensorMap c0, ix, iy;  // per-warp constants [B]: box 128xH
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void bulk_row(void *dst_smem, const float *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void tma_box(void *dst_smem, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
 }
 
 template <int DATA>
-__global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS_CSAD : FALDOI_TT_CTAS) tv_tile_kernel(TvArgs a, int it) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+__global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS_CSAD : FALDOI_TT_CTAS) tv_tile_kernel(const __grid_constant__ TileMaps maps, TvArgs a, int it) {
+    extern __shared__ unsigned char smem_raw[];
+    TileSmem &S = *reinterpret_cast<TileSmem *>(((size_t)smem_raw + 127) & ~(size_t)127);
     const int b = blockIdx.z;
     if (!pair_active<DATA>(a, b, it)) return;
 
@@ -67,10 +92,7 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
 
     const int par = (a.parity[b] + it) & 1;
     const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
-    const float *in = a.state + (size_t)par * a.set_stride + (size_t)b * plane;
     float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
-    const float *c0 = (DATA == DATA_TVL1 ? a.rho_c : a.scale) + (size_t)b * plane;
-    const float *cIx = a.Ix + (size_t)b * plane, *cIy = a.Iy + (size_t)b * plane;
 
     // CSAD: this thread's phase-2 quad is known now; fetch its four rank hints (one 4-byte load) and
     // the two probe values per pixel before anything else, so their latency hides behind the
@@ -93,37 +115,23 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         }
     }
 
-    // ---- stage the tile: thread 0 arms the barrier, then one row segment per thread ----
-    const int ub_lo = (y0 > 0) ? -1 : 0, ub_hi = min(TT_H, h - 1 - y0);  // ubar rows (relative) lo..hi inclusive
+    // ---- stage the tile: one thread arms the mbarrier and issues the 11 TMA box loads ----
+    const int ub_lo = (y0 > 0) ? -1 : 0;
     const int xi_lo = ub_lo, xi_hi = rows - 1;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        const unsigned total = (unsigned)(2 * (ub_hi - ub_lo + 1) + 4 * (xi_hi - xi_lo + 1)) * TT_PW * 4u + (unsigned)(5 * rows) * TT_W * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"(total) : "memory");
-    }
-    __syncthreads();
-    {
-        // job list: [0, 2*18) ubar rows, [36, 36+4*17) xi rows, [104, 104+5*16) plain rows
-        for (int j = tid; j < 2 * (TT_H + 2) + 4 * (TT_H + 1) + 5 * TT_H; j += TT_THREADS) {
-            if (j < 2 * (TT_H + 2)) {
-                const int k = j / (TT_H + 2), r = j % (TT_H + 2) - 1;
-                if (r >= ub_lo && r <= ub_hi)
-                    bulk_row(&S.ub[k][r + 1][0], in + (ST_UB1 + k) * ks + (size_t)(y0 + r) * pitch + x0 - 4, TT_PW * 4, &S.bar);
-            } else if (j < 2 * (TT_H + 2) + 4 * (TT_H + 1)) {
-                const int jj = j - 2 * (TT_H + 2);
-                const int k = jj / (TT_H + 1), r = jj % (TT_H + 1) - 1;
-                if (r >= xi_lo && r <= xi_hi)
-                    bulk_row(&S.xi[k][r + 1][0], in + (ST_XI11 + k) * ks + (size_t)(y0 + r) * pitch + x0 - 4, TT_PW * 4, &S.bar);
-            } else {
-                const int jj = j - 2 * (TT_H + 2) - 4 * (TT_H + 1);
-                const int k = jj / TT_H, r = jj % TT_H;
-                if (r < rows) {
-                    const float *src = (k == 0) ? in + ST_U1 * ks : (k == 1) ? in + ST_U2 * ks : (k == 2) ? c0 : (k == 3) ? cIx : cIy;
-                    bulk_row(&S.pl[k][r][0], src + (size_t)(y0 + r) * pitch + x0, TT_W * 4, &S.bar);
-                }
-            }
-        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"((unsigned)TT_TX_BYTES) : "memory");
+        const int B = a.g.B, zs = par * ST_COUNT * B + b;
+        tma_box(S.ub(0, 0), &maps.ub, x0 - 4, y0 - 1, zs + ST_UB1 * B, &S.bar);
+        tma_box(S.ub(1, 0), &maps.ub, x0 - 4, y0 - 1, zs + ST_UB2 * B, &S.bar);
+#pragma unroll
+        for (int k = 0; k < 4; k++) tma_box(S.xi(k, 0), &maps.xi, x0 - 4, y0 - 1, zs + (ST_XI11 + k) * B, &S.bar);
+        tma_box(S.pl(0, 0), &maps.pl, x0, y0, zs + ST_U1 * B, &S.bar);
+        tma_box(S.pl(1, 0), &maps.pl, x0, y0, zs + ST_U2 * B, &S.bar);
+        tma_box(S.pl(2, 0), &maps.c0, x0, y0, b, &S.bar);
+        tma_box(S.pl(3, 0), &maps.ix, x0, y0, b, &S.bar);
+        tma_box(S.pl(4, 0), &maps.iy, x0, y0, b, &S.bar);
     }
     // wait for the bytes (phase 0): one thread polls the mbarrier, the other warps sleep on the CTA
     // barrier instead of burning issue slots in a spin loop (the acquire of the poller is carried
@@ -152,20 +160,20 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         const int gx0 = x0 + 4 * q;
         if (gx0 + 3 < 0 || gx0 >= w) continue;
         const bool ylast = (y + yo == hg - 1);
-        const float4 B1 = *reinterpret_cast<const float4 *>(&S.ub[0][r + 1][cx]);
-        const float4 B2 = *reinterpret_cast<const float4 *>(&S.ub[1][r + 1][cx]);
-        const float b1[5] = {B1.x, B1.y, B1.z, B1.w, S.ub[0][r + 1][cx + 4]};
-        const float b2[5] = {B2.x, B2.y, B2.z, B2.w, S.ub[1][r + 1][cx + 4]};
+        const float4 B1 = *reinterpret_cast<const float4 *>(S.ub(0, r + 1) + cx);
+        const float4 B2 = *reinterpret_cast<const float4 *>(S.ub(1, r + 1) + cx);
+        const float b1[5] = {B1.x, B1.y, B1.z, B1.w, S.ub(0, r + 1)[cx + 4]};
+        const float b2[5] = {B2.x, B2.y, B2.z, B2.w, S.ub(1, r + 1)[cx + 4]};
         float4 N1 = make_float4(0.f, 0.f, 0.f, 0.f), N2 = N1;
         if (!ylast) {
-            N1 = *reinterpret_cast<const float4 *>(&S.ub[0][r + 2][cx]);
-            N2 = *reinterpret_cast<const float4 *>(&S.ub[1][r + 2][cx]);
+            N1 = *reinterpret_cast<const float4 *>(S.ub(0, r + 2) + cx);
+            N2 = *reinterpret_cast<const float4 *>(S.ub(1, r + 2) + cx);
         }
         const float n1[4] = {N1.x, N1.y, N1.z, N1.w}, n2[4] = {N2.x, N2.y, N2.z, N2.w};
-        float4 X11 = *reinterpret_cast<const float4 *>(&S.xi[0][r + 1][cx]);
-        float4 X12 = *reinterpret_cast<const float4 *>(&S.xi[1][r + 1][cx]);
-        float4 X21 = *reinterpret_cast<const float4 *>(&S.xi[2][r + 1][cx]);
-        float4 X22 = *reinterpret_cast<const float4 *>(&S.xi[3][r + 1][cx]);
+        float4 X11 = *reinterpret_cast<const float4 *>(S.xi(0, r + 1) + cx);
+        float4 X12 = *reinterpret_cast<const float4 *>(S.xi(1, r + 1) + cx);
+        float4 X21 = *reinterpret_cast<const float4 *>(S.xi(2, r + 1) + cx);
+        float4 X22 = *reinterpret_cast<const float4 *>(S.xi(3, r + 1) + cx);
         float x11[4] = {X11.x, X11.y, X11.z, X11.w}, x12[4] = {X12.x, X12.y, X12.z, X12.w};
         float x21[4] = {X21.x, X21.y, X21.z, X21.w}, x22[4] = {X22.x, X22.y, X22.z, X22.w};
         // forward differences of ubar (zero on the last column / row of the FRAME), then
@@ -203,10 +211,10 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
                 x22[k] /= d2;
             }
         }
-        *reinterpret_cast<float4 *>(&S.xi[0][r + 1][cx]) = make_float4(x11[0], x11[1], x11[2], x11[3]);
-        *reinterpret_cast<float4 *>(&S.xi[1][r + 1][cx]) = make_float4(x12[0], x12[1], x12[2], x12[3]);
-        *reinterpret_cast<float4 *>(&S.xi[2][r + 1][cx]) = make_float4(x21[0], x21[1], x21[2], x21[3]);
-        *reinterpret_cast<float4 *>(&S.xi[3][r + 1][cx]) = make_float4(x22[0], x22[1], x22[2], x22[3]);
+        *reinterpret_cast<float4 *>(S.xi(0, r + 1) + cx) = make_float4(x11[0], x11[1], x11[2], x11[3]);
+        *reinterpret_cast<float4 *>(S.xi(1, r + 1) + cx) = make_float4(x12[0], x12[1], x12[2], x12[3]);
+        *reinterpret_cast<float4 *>(S.xi(2, r + 1) + cx) = make_float4(x21[0], x21[1], x21[2], x21[3]);
+        *reinterpret_cast<float4 *>(S.xi(3, r + 1) + cx) = make_float4(x22[0], x22[1], x22[2], x22[3]);
     }
     __syncthreads();
 
@@ -220,18 +228,18 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         if (gx0 >= pitch || y < a.g.own_lo || y >= a.g.own_hi) continue;  // halo rows belong to the neighbour stripe
         const int gy = y + yo;
         const bool interior = gx0 > 0 && gx0 + 4 < w && gy > 0 && gy < hg - 1;  // no frame border in this quad
-        const float4 M11 = *reinterpret_cast<const float4 *>(&S.xi[0][r + 1][cx]);
-        const float4 M12 = *reinterpret_cast<const float4 *>(&S.xi[1][r + 1][cx]);
-        const float4 M21 = *reinterpret_cast<const float4 *>(&S.xi[2][r + 1][cx]);
-        const float4 M22 = *reinterpret_cast<const float4 *>(&S.xi[3][r + 1][cx]);
-        const float4 T12 = *reinterpret_cast<const float4 *>(&S.xi[1][r][cx]);
-        const float4 T22 = *reinterpret_cast<const float4 *>(&S.xi[3][r][cx]);
-        const float l11 = S.xi[0][r + 1][cx - 1], l21 = S.xi[2][r + 1][cx - 1];
-        const float4 U1 = *reinterpret_cast<const float4 *>(&S.pl[0][r][4 * q]);
-        const float4 U2 = *reinterpret_cast<const float4 *>(&S.pl[1][r][4 * q]);
-        const float4 C0 = *reinterpret_cast<const float4 *>(&S.pl[2][r][4 * q]);
-        const float4 IX = *reinterpret_cast<const float4 *>(&S.pl[3][r][4 * q]);
-        const float4 IY = *reinterpret_cast<const float4 *>(&S.pl[4][r][4 * q]);
+        const float4 M11 = *reinterpret_cast<const float4 *>(S.xi(0, r + 1) + cx);
+        const float4 M12 = *reinterpret_cast<const float4 *>(S.xi(1, r + 1) + cx);
+        const float4 M21 = *reinterpret_cast<const float4 *>(S.xi(2, r + 1) + cx);
+        const float4 M22 = *reinterpret_cast<const float4 *>(S.xi(3, r + 1) + cx);
+        const float4 T12 = *reinterpret_cast<const float4 *>(S.xi(1, r) + cx);
+        const float4 T22 = *reinterpret_cast<const float4 *>(S.xi(3, r) + cx);
+        const float l11 = S.xi(0, r + 1)[cx - 1], l21 = S.xi(2, r + 1)[cx - 1];
+        const float4 U1 = *reinterpret_cast<const float4 *>(S.pl(0, r) + 4 * q);
+        const float4 U2 = *reinterpret_cast<const float4 *>(S.pl(1, r) + 4 * q);
+        const float4 C0 = *reinterpret_cast<const float4 *>(S.pl(2, r) + 4 * q);
+        const float4 IX = *reinterpret_cast<const float4 *>(S.pl(3, r) + 4 * q);
+        const float4 IY = *reinterpret_cast<const float4 *>(S.pl(4, r) + 4 * q);
         const float m11[4] = {M11.x, M11.y, M11.z, M11.w}, m12[4] = {M12.x, M12.y, M12.z, M12.w};
         const float m21[4] = {M21.x, M21.y, M21.z, M21.w}, m22[4] = {M22.x, M22.y, M22.z, M22.w};
         const float p12[4] = {T12.x, T12.y, T12.z, T12.w}, p22[4] = {T22.x, T22.y, T22.z, T22.w};
