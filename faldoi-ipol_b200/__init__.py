@@ -50,7 +50,7 @@ EXPORTS = [
     "faldoi_nltvl1_PD", "faldoi_nltvcsad_PD", "faldoi_guided_tvl2coupled_occ", "faldoi_centered_gradient",
     "faldoi_bicubic_warp", "faldoi_stripe_rows", "faldoi_stripes_create", "faldoi_stripes_destroy",
     "faldoi_stripes_upload", "faldoi_stripes_run", "faldoi_stripes_download", "faldoi_stripes_last_run_ms",
-    "faldoi_stripes_last_launches",
+    "faldoi_stripes_last_launches", "faldoi_selftest_division",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
         L.faldoi_stripes_last_run_ms.restype = C.c_float
         L.faldoi_stripes_last_launches.argtypes = [vp]
         L.faldoi_stripes_last_launches.restype = C.c_longlong
+        L.faldoi_selftest_division.argtypes = [i, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
         _lib = L
     return _lib
 
@@ -291,6 +292,13 @@ def nltvcsad_PD(I0, I1, a, pd, lambda_, theta, tau, w, h, warps, verbose, u1, u2
 def guided_tvl2coupled_occ(I0, I1, I_1, u1, u2, chi, params, nx, ny, verbose=0):
     _check(lib().faldoi_guided_tvl2coupled_occ(_ptr(I0), _ptr(I1), _ptr(I_1), _ptr(u1), _ptr(u2), _ptr(chi),
                                                C.byref(params), int(nx), int(ny), int(verbose)))
+
+
+def selftest_division(n=1 << 28, seed=1, device=0):
+    """Mismatches between the shared-reciprocal division and IEEE division over n operand pairs (x4 quotients)."""
+    bad = C.c_ulonglong(0)
+    _check(lib().faldoi_selftest_division(device, n, seed, C.byref(bad)))
+    return bad.value
 
 
 def centered_gradient(f, device=0):

@@ -1009,3 +1009,17 @@ extern "C" int faldoi_bicubic_warp(int device, const float *in, const float *u, 
 }
 
 #include "stripes.inc"
+
+// Self-test of the shared-reciprocal division against IEEE division (see common.cuh).
+extern "C" int faldoi_selftest_division(int device, unsigned long long n, unsigned long long seed, unsigned long long *mismatches) {
+    if (!mismatches) return FALDOI_ERR_ARG;
+    FALDOI_CUDA(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    FALDOI_CUDA(cudaMalloc(&d, sizeof(*d)));
+    FALDOI_CUDA(cudaMemset(d, 0, sizeof(*d)));
+    selftest_division_kernel<<<148 * 8, 256>>>(n, seed, d);
+    cudaError_t e = cudaMemcpy(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    FALDOI_CUDA(e);
+    return FALDOI_OK;
+}

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
     extern __shared__ unsigned char smem_raw[];
     TileSmem &S = *reinterpret_cast<TileSmem *>(((size_t)smem_raw + 127) & ~(size_t)127);
     const int b = blockIdx.z;
+    const int par0 = a.parity[b];  // issued together with the error word read by pair_active: one L2 round trip
     if (!pair_active<DATA>(a, b, it)) return;
 
     const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
     const int tid = threadIdx.x;
     const int rows = min(TT_H, h - y0);  // interior rows of this tile that exist
 
-    const int par = (a.parity[b] + it) & 1;
+    const int par = (par0 + it) & 1;
     const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
     float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
 
@@ -204,11 +205,15 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         if (big > 1.f) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const float d1 = fmaxf(1.f, nr1[k]), d2 = fmaxf(1.f, nr2[k]);
-                x11[k] /= d1;
-                x12[k] /= d1;
-                x21[k] /= d2;
-                x22[k] /= d2;
+                if (DATA == DATA_TVL1) {
+                    if (nr1[k] > 1.f) div4_shared(x11[k], x12[k], x21[k], x22[k], nr1[k]);
+                } else {
+                    const float d1 = fmaxf(1.f, nr1[k]), d2 = fmaxf(1.f, nr2[k]);
+                    x11[k] /= d1;
+                    x12[k] /= d1;
+                    x21[k] /= d2;
+                    x22[k] /= d2;
+                }
             }
         }
         *reinterpret_cast<float4 *>(S.xi(0, r + 1) + cx) = make_float4(x11[0], x11[1], x11[2], x11[3]);

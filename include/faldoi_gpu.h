@@ -168,6 +168,10 @@ int faldoi_centered_gradient(int device, const float *in, float *dx, float *dy, 
 int faldoi_bicubic_warp(int device, const float *in, const float *u, const float *v, float *out, int nx, int ny,
                         int border_out);
 
+/* Numerical self-test: the shared-reciprocal division used by the TVL2 dual projection against
+ * IEEE division on n pseudo-random / structured operand pairs; *mismatches must come back 0. */
+int faldoi_selftest_division(int device, unsigned long long n, unsigned long long seed, unsigned long long *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,3 +132,10 @@ def test_fullsize_reference_pair(fb, po):
     assert round(epe, 3) == round(float(g["epe_out"]), 3) == 0.223
     if os.path.exists(os.path.join(D, "var_m0.flo")):
         assert np.array_equal(u, po.read_flo(os.path.join(D, "var_m0.flo")))
+
+
+def test_shared_reciprocal_division_is_ieee(fb):
+    """The 4-quotients-one-reciprocal division of the TVL2 dual projection must equal IEEE division
+    bit for bit on its guarded range: 2^31 quotients, random and structured significands."""
+    for seed in (1, 2):
+        assert fb.selftest_division(1 << 28, seed) == 0
