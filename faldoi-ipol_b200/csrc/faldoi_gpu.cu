@@ -709,10 +709,23 @@ static int occ_upload(faldoi_solver *s, int slot, const float *Im1, const float 
     return FALDOI_OK;
 }
 
+// sweeps fused per launch by the temporally blocked OCC kernels: 24/NS launches, which must be an
+// even number so the ping-pong ends in set 0 where the u-update / next outer iteration read
+#ifndef FALDOI_OCC_NS
+#define FALDOI_OCC_NS 4
+#endif
+enum { OCC_NS = FALDOI_OCC_NS };
+static_assert(24 % OCC_NS == 0 && (24 / OCC_NS) % 2 == 0, "24/OCC_NS must be an even integer");
+
 static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
     const Geo g = s->g;
     const dim3 blk(32, 8);
     const dim3 grd = grid2d(g, blk, npairs);
+    const dim3 mgrd((g.w + OM_TW - 1) / OM_TW, (g.h + OM_TH - 1) / OM_TH, npairs);
+    static const bool fused = [] {
+        const char *e = getenv("FALDOI_OCC_FUSED");  // "0" selects the one-sweep-per-launch kernels
+        return !(e && e[0] == '0');
+    }();
     OccArgs a{};
     a.pl = s->occ;
     a.I0 = s->I0;
@@ -742,10 +755,20 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         for (int it = 0; it < p->max_iters; it++) {
             occ_v_kernel<<<grd, blk, 0, s->stream>>>(a, it);
-            for (int k = 0; k < 24; k++) occ_xi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1);
+            if (fused) {
+                for (int k = 0; k < 24 / OCC_NS; k++) occ_xi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1);
+            } else {
+                for (int k = 0; k < 24; k++) occ_xi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1);
+            }
             occ_u_kernel<<<grd, blk, 0, s->stream>>>(a, it);
-            for (int k = 0; k < 24; k++) occ_chi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1, k == 23);
-            s->launches += 50;
+            if (fused) {
+                for (int k = 0; k < 24 / OCC_NS; k++)
+                    occ_chi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
+                s->launches += 2 + 2 * (24 / OCC_NS);
+            } else {
+                for (int k = 0; k < 24; k++) occ_chi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1, k == 23);
+                s->launches += 50;
+            }
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, 0, 0, nullptr, s->log_iters,
