@@ -99,7 +99,7 @@ struct NlArgs {
 // Launch `it` reads set (it&1) and writes set (it&1)^1: NLTV always runs all
 // max_iters iterations (:1249), so the parity is the same for every pair.
 template <int DATA>
-__global__ void __launch_bounds__(256) nltv_iter_kernel(NlArgs a, int it, int base_parity) {
+__global__ void __launch_bounds__(256, 4) nltv_iter_kernel(NlArgs a, int it, int base_parity) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int b = blockIdx.z;
@@ -156,36 +156,49 @@ __global__ void __launch_bounds__(256) nltv_iter_kernel(NlArgs a, int it, int ba
         }
 
         // ---- dual update + non-local divergence ----
+        // Pixels at least 2 away from every frame border (all 24 neighbours exist) take a loop without
+        // bounds tests; 1/wt is formed once per pixel (the NLTV models are tolerance-level, see NL_DIV).
         float dP = 0.f, dQ = 0.f;
+        const float rwtp = NL_DIV(1.f, wtp);
+        const float *ub1p = sin + ST_UB1 * ks, *ub2p = sin + ST_UB2 * ks;
+        const float *wtb = a.wt + off;
+        auto slot = [&](int s, int q) {
+            const float wv = a.wgt[(size_t)s * ks + off + p];
+            const float q1 = ub1p[q], q2 = ub2p[q];
+            const float rwtq = NL_DIV(1.f, wtb[q]);
+            const float t1 = wv * (c1 - q1), t2 = wv * (c2 - q2);
+            // own dual, slot s
+            const float g1 = t1 * rwtp, g2 = t2 * rwtp;
+            const float Pn = NL_DIV(din[(size_t)s * ks + p] + tau * g1, 1 + tau * fabsf(g1));
+            const float Qn = NL_DIV(din[(size_t)(NL_SLOTS + s) * ks + p] + tau * g2, 1 + tau * fabsf(g2));
+            dout[(size_t)s * ks + p] = Pn;
+            dout[(size_t)(NL_SLOTS + s) * ks + p] = Qn;
+            // neighbour's reciprocal dual, slot 23-s at q (its difference is the negated one)
+            const int rs = NL_SLOTS - 1 - s;
+            const float h1 = -t1 * rwtq, h2 = -t2 * rwtq;
+            const float Pr = NL_DIV(din[(size_t)rs * ks + q] + tau * h1, 1 + tau * fabsf(h1));
+            const float Qr = NL_DIV(din[(size_t)(NL_SLOTS + rs) * ks + q] + tau * h2, 1 + tau * fabsf(h2));
+            dP += wv * (Pn - Pr);
+            dQ += wv * (Qn - Qr);
+        };
+        if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {
 #pragma unroll
-        for (int s = 0; s < NL_SLOTS; s++) {
-            int k, l;
-            nl_slot_offset(s, k, l);
-            const int r = y + k, c = x + l;
-            if (c >= 0 && c < w && r >= 0 && r < h) {
-                const int q = r * pitch + c;
-                const float wv = a.wgt[(size_t)s * ks + off + p];
-                const float q1 = sin[ST_UB1 * ks + q], q2 = sin[ST_UB2 * ks + q];
-                const float wtq = a.wt[off + q];
-                // own dual, slot s
-                const float g1 = NL_DIV(wv * (c1 - q1), wtp);
-                const float Pn = NL_DIV(din[(size_t)s * ks + p] + tau * g1, 1 + tau * fabsf(g1));
-                const float g2 = NL_DIV(wv * (c2 - q2), wtp);
-                const float Qn = NL_DIV(din[(size_t)(NL_SLOTS + s) * ks + p] + tau * g2, 1 + tau * fabsf(g2));
-                dout[(size_t)s * ks + p] = Pn;
-                dout[(size_t)(NL_SLOTS + s) * ks + p] = Qn;
-                // neighbour's reciprocal dual, slot 23-s at q
-                const int rs = NL_SLOTS - 1 - s;
-                const float h1 = NL_DIV(wv * (q1 - c1), wtq);
-                const float Pr = NL_DIV(din[(size_t)rs * ks + q] + tau * h1, 1 + tau * fabsf(h1));
-                const float h2 = NL_DIV(wv * (q2 - c2), wtq);
-                const float Qr = NL_DIV(din[(size_t)(NL_SLOTS + rs) * ks + q] + tau * h2, 1 + tau * fabsf(h2));
-                dP += wv * (Pn - Pr);
-                dQ += wv * (Qn - Qr);
+            for (int s = 0; s < NL_SLOTS; s++) {
+                int k, l;
+                nl_slot_offset(s, k, l);
+                slot(s, p + k * pitch + l);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NL_SLOTS; s++) {
+                int k, l;
+                nl_slot_offset(s, k, l);
+                const int r = y + k, c = x + l;
+                if (c >= 0 && c < w && r >= 0 && r < h) slot(s, r * pitch + c);
             }
         }
-        dP /= wtp;
-        dQ /= wtp;
+        dP *= rwtp;
+        dQ *= rwtp;
 
         // ---- primal step (+div) and extrapolation ----
         const float o1 = u1 - tau * (dP + div_const(u1 - v1, a.dth));
