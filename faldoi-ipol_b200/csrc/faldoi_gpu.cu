@@ -204,6 +204,14 @@ static int make_tile_maps(faldoi_solver *s) {
     if ((rc = make_plane_map(&s->maps.c0, c0, g, g.B, TT_W, TT_H))) return rc;
     if ((rc = make_plane_map(&s->maps.ix, s->Ix, g, g.B, TT_W, TT_H))) return rc;
     if ((rc = make_plane_map(&s->maps.iy, s->Iy, g, g.B, TT_W, TT_H))) return rc;
+    if (!method_is_csad(s->method)) {  // boxes of the two-iteration kernel (2-pixel apron)
+        if ((rc = make_plane_map(&s->maps2.ub, s->state, g, nstate, TT_PW, T2_UB_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.xi, s->state, g, nstate, TT_PW, T2_XI_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.pl, s->state, g, nstate, TT_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.c0, c0, g, g.B, TT_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.ix, s->Ix, g, g.B, TT_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.iy, s->Iy, g, g.B, TT_PW, T2_PL_ROWS))) return rc;
+    }
     return FALDOI_OK;
 }
 
@@ -307,6 +315,8 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
     if (!cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
+                 "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(tv_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
                  "cudaFuncSetAttribute"))
         return fail(FALDOI_ERR_CUDA);
     if (!cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize")) return fail(FALDOI_ERR_CUDA);
@@ -377,7 +387,7 @@ extern "C" int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0,
 // ---------------------------------------------------------------------------
 __global__ void finalize_warp_kernel(const unsigned *err_max, const double *err_sum, int use_sum, int always_all,
                                      int *parity, int *log_iters, float *log_err, int max_iters, float tol2,
-                                     float npix, int warp_idx, int npairs) {
+                                     float npix, int warp_idx, int npairs, int iters_per_flip = 1) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= npairs) return;
     int n = 0;
@@ -387,7 +397,8 @@ __global__ void finalize_warp_kernel(const unsigned *err_max, const double *err_
         n++;
         if (!always_all && !(e > tol2)) break;
     }
-    if (parity) parity[b] = (parity[b] + n) & 1;
+    // ping-pong flips: one per iteration, or one per launch of the two-iteration kernel (ceil(n/2))
+    if (parity) parity[b] = (parity[b] + (n + iters_per_flip - 1) / iters_per_flip) & 1;
     log_iters[b * FALDOI_MAX_WARPS + warp_idx] = n;
     log_err[b * FALDOI_MAX_WARPS + warp_idx] = e;
 }
@@ -399,6 +410,20 @@ __global__ void count_active_kernel(const unsigned *err_max, const double *err_s
     for (int b = 0; b < npairs; b++) {
         const float e = use_sum ? (float)err_sum[(size_t)b * max_iters + it] / npix : __uint_as_float(err_max[(size_t)b * max_iters + it]);
         n += (e > tol2);
+    }
+    *out = n;
+}
+
+// same for the two-iteration kernel after its launch L: a pair keeps iterating iff that launch ran
+// normally and both of its iterations still exceed the tolerance
+__global__ void count_active2_kernel(const unsigned *err_max, const unsigned char *stat, int stat_stride, int npairs, int max_iters,
+                                     int L, float tol2, int *out) {
+    int n = 0;
+    for (int b = 0; b < npairs; b++) {
+        const unsigned *e = err_max + (size_t)b * max_iters + 2 * L;
+        bool act = stat[(size_t)b * stat_stride + L] && __uint_as_float(e[0]) > tol2;
+        if (act && 2 * L + 1 < max_iters) act = __uint_as_float(e[1]) > tol2;
+        n += act;
     }
     *out = n;
 }
@@ -508,6 +533,20 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.tol2 = p->tol * p->tol;
     if (int rc = make_div_const(s, p->theta, &a.dth)) return rc;
     const int R = pick_rows(g, npairs);
+    // TVL2 runs two iterations per HBM pass (tv_tile2_kernel) unless FALDOI_TV_T2=0
+    static const bool t2_env = [] {
+        const char *e = getenv("FALDOI_TV_T2");
+        return !(e && e[0] == '0');
+    }();
+    const bool use_t2 = !csad && use_tile_kernel() && t2_env;
+    if (use_t2) {
+        const int need = p->max_iters / 2 + 4;
+        if (need > s->t2_stride) {
+            s->t2_stat = (unsigned char *)s->dmalloc(((size_t)g.B * need + 3) / 4);
+            if (!s->t2_stat) return FALDOI_ERR_MEM;
+            s->t2_stride = need;
+        }
+    }
     for (int wp = 0; wp < p->warps; wp++) {
         if (csad)
             FALDOI_CUDA(cudaMemsetAsync(s->err_sum, 0, (size_t)g.B * p->max_iters * sizeof(double), s->stream));
@@ -557,8 +596,32 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         // once.  To stop enqueuing once EVERY pair has met the exit test, the active-pair count is
         // copied to pinned memory every CHUNK launches and inspected two chunks later (so the GPU
         // always has at least one full chunk queued and never waits for the host).
+        if (use_t2) {
+            // two iterations per launch: ceil(max_iters/2) launches + one slot for a trailing fix-up
+            const int nL = (p->max_iters + 1) / 2 + 1, LCHUNK = 13;
+            FALDOI_CUDA(cudaMemsetAsync(s->t2_stat, 0, (size_t)g.B * s->t2_stride, s->stream));
+            const dim3 grid((g.pitch + TT_W - 1) / TT_W, (g.h + TT_H - 1) / TT_H, npairs);
+            T2Args t2{s->t2_stat, s->t2_stride};
+            for (int c = 0, L = 0; L < nL; c++) {
+                if (c >= 2) {
+                    FALDOI_CUDA(cudaEventSynchronize(s->chunk_ev[(c - 2) & 3]));
+                    if (s->h_active[(c - 2) & 3] == 0) break;
+                }
+                const int end = (L + LCHUNK < nL) ? L + LCHUNK : nL;
+                for (; L < end; L++) {
+                    tv_tile2_kernel<<<grid, TT_THREADS, sizeof(Tile2Smem) + 128, s->stream>>>(s->maps2, a, t2, L);
+                    s->launches++;
+                }
+                const int Lc = (L - 1 < (p->max_iters + 1) / 2) ? L - 1 : (p->max_iters + 1) / 2 - 1;
+                count_active2_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->t2_stat, s->t2_stride, npairs, p->max_iters, Lc, a.tol2,
+                                                             s->d_active + (c & 3));
+                FALDOI_CUDA(cudaMemcpyAsync(s->h_active + (c & 3), s->d_active + (c & 3), sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+                FALDOI_CUDA(cudaEventRecord(s->chunk_ev[c & 3], s->stream));
+                s->launches++;
+            }
+        }
         const int CHUNK = 25;
-        for (int c = 0, it = 0; it < p->max_iters; c++) {
+        for (int c = 0, it = 0; !use_t2 && it < p->max_iters; c++) {
             if (c >= 2) {
                 FALDOI_CUDA(cudaEventSynchronize(s->chunk_ev[(c - 2) & 3]));
                 if (s->h_active[(c - 2) & 3] == 0) break;
@@ -580,7 +643,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, 0, s->parity,
                                                                        s->log_iters, s->log_err, p->max_iters, a.tol2,
-                                                                       (float)(g.w * g.h), wp, npairs);
+                                                                       (float)(g.w * g.h), wp, npairs, use_t2 ? 2 : 1);
         s->launches++;
     }
     export_flow_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->state, s->set_stride, s->parity, s->packed, g);

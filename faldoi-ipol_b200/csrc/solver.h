@@ -8,6 +8,7 @@
 #include "../../include/faldoi_gpu.h"
 #include "common.cuh"
 #include "tv_tile_kernel.cuh"
+#include "tv_tile2_kernel.cuh"
 
 namespace faldoi {
 
@@ -43,6 +44,9 @@ struct faldoi_solver {
     float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr, *bs = nullptr;
     unsigned char *csad_hint = nullptr;  // [B][plane] bytes
     faldoi::TileMaps maps{};             // TMA descriptors of the tile kernel (TV family)
+    faldoi::Tile2Maps maps2{};           // ... of the two-iteration TVL2 kernel
+    unsigned char *t2_stat = nullptr;    // [B][t2_stride] launch status of the two-iteration kernel
+    int t2_stride = 0;
     // NLTV: Lab, weights, duals
     float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *dual = nullptr;
     size_t dual_set_stride = 0;

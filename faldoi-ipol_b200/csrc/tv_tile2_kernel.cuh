@@ -1,0 +1,311 @@
+// Temporally blocked TVL2 iteration: TWO primal-dual iterations per pass over HBM.
+//
+// Same arithmetic as tv_tile_kernel<DATA_TVL1> (see tv_kernels.cuh for the reference citations),
+// but a CTA stages its 128x8 tile with a 2-pixel apron, runs iteration A on the apron-extended
+// region entirely in shared memory, then iteration B on the tile, and writes the 8 state planes
+// once: 41 instead of 76 bytes of HBM traffic per pixel and iteration for 14 % more arithmetic.
+//
+//   staged (TMA boxes, cols x0-4 .. x0+131):   ubar  rows y0-2 .. y0+9
+//                                              xi    rows y0-2 .. y0+8
+//                                              u, rho_c, Ix, Iy   rows y0-1 .. y0+8
+//   1A  xi_A   rows y0-2 .. y0+8      2A  u_A, ubar_A (in smem)  rows y0-1 .. y0+8, err(2L) over the tile
+//   1B  xi_B   rows y0-1 .. y0+7      2B  u_B, ubar_B, xi_B -> HBM, rows y0 .. y0+7, err(2L+1)
+//
+// Exit test.  Launch L runs iterations 2L and 2L+1 of a warp.  The reference stops after the
+// first iteration whose error is <= tol^2; if that is the FIRST iteration of a launch, the launch
+// has already applied one iteration too many.  Nothing is lost: the launch read set P and wrote set
+// P^1, so set P still holds its input.  The next launch slot sees err(2L) <= tol^2 and, instead of
+// iterating, redoes that single iteration from set P into set P^1 ("fix-up", no error update).
+// stat[b][L] records whether launch L ran normally, so every launch decides from O(1) words.
+#pragma once
+#include "tv_tile_kernel.cuh"
+
+namespace faldoi {
+
+enum {
+    T2_UB_ROWS = TT_H + 4,
+    T2_XI_ROWS = TT_H + 3,
+    T2_PL_ROWS = TT_H + 2,
+    T2_UB_FLOATS = (T2_UB_ROWS * TT_PW + 31) / 32 * 32,
+    T2_XI_FLOATS = (T2_XI_ROWS * TT_PW + 31) / 32 * 32,
+    T2_PL_FLOATS = (T2_PL_ROWS * TT_PW + 31) / 32 * 32,
+    T2_TX_BYTES = (2 * T2_UB_ROWS + 4 * T2_XI_ROWS + 5 * T2_PL_ROWS) * TT_PW * 4,
+    T2_QUADS = TT_PW / 4  // 34 column quads: smem columns 0..135 <-> x0-4 .. x0+131
+};
+
+struct Tile2Smem {
+    float ub_[2][T2_UB_FLOATS];  // row index = relative row + 2
+    float xi_[4][T2_XI_FLOATS];  // row index = relative row + 2
+    float pl_[5][T2_PL_FLOATS];  // u1, u2, rho_c, Ix, Iy; row index = relative row + 1
+    float red[2][TT_THREADS / 32];
+    unsigned long long bar;
+    __device__ __forceinline__ float *ub(int k, int r) { return &ub_[k][(r + 2) * TT_PW]; }
+    __device__ __forceinline__ float *xi(int k, int r) { return &xi_[k][(r + 2) * TT_PW]; }
+    __device__ __forceinline__ float *pl(int k, int r) { return &pl_[k][(r + 1) * TT_PW]; }
+};
+
+struct Tile2Maps {
+    CUtensorMap ub, xi, pl;  // state array, boxes 136 x {12, 11, 10}
+    CUtensorMap c0, ix, iy;  // rho_c, Ix, Iy: box 136 x 10
+};
+
+enum { T2_MODE_SKIP = 0, T2_MODE_TWO = 1, T2_MODE_ONE = 2, T2_MODE_FIXUP = 3 };
+
+// dual step of one column quad of relative row r, in place in shared memory
+__device__ __forceinline__ void t2_dual_quad(Tile2Smem &S, int r, int qi, int gx0, int gy, int w, int hg, float tau) {
+    const int cx = 4 * qi;
+    const bool ylast = (gy == hg - 1);
+    const float4 B1 = *reinterpret_cast<const float4 *>(S.ub(0, r) + cx);
+    const float4 B2 = *reinterpret_cast<const float4 *>(S.ub(1, r) + cx);
+    const bool has_r = (cx + 4 < TT_PW);  // the last quad of the staged row has no right neighbour in smem (its value is never needed)
+    const float b1[5] = {B1.x, B1.y, B1.z, B1.w, has_r ? S.ub(0, r)[cx + 4] : 0.f};
+    const float b2[5] = {B2.x, B2.y, B2.z, B2.w, has_r ? S.ub(1, r)[cx + 4] : 0.f};
+    float4 N1 = make_float4(0.f, 0.f, 0.f, 0.f), N2 = N1;
+    if (!ylast) {
+        N1 = *reinterpret_cast<const float4 *>(S.ub(0, r + 1) + cx);
+        N2 = *reinterpret_cast<const float4 *>(S.ub(1, r + 1) + cx);
+    }
+    const float n1[4] = {N1.x, N1.y, N1.z, N1.w}, n2[4] = {N2.x, N2.y, N2.z, N2.w};
+    const float4 X11 = *reinterpret_cast<const float4 *>(S.xi(0, r) + cx);
+    const float4 X12 = *reinterpret_cast<const float4 *>(S.xi(1, r) + cx);
+    const float4 X21 = *reinterpret_cast<const float4 *>(S.xi(2, r) + cx);
+    const float4 X22 = *reinterpret_cast<const float4 *>(S.xi(3, r) + cx);
+    float x11[4] = {X11.x, X11.y, X11.z, X11.w}, x12[4] = {X12.x, X12.y, X12.z, X12.w};
+    float x21[4] = {X21.x, X21.y, X21.z, X21.w}, x22[4] = {X22.x, X22.y, X22.z, X22.w};
+    const bool full = (gx0 + 4 < w);
+    float nr[4];
+    float big = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float u1x = (full || gx0 + k < w - 1) ? b1[k + 1] - b1[k] : 0.f;
+        const float u2x = (full || gx0 + k < w - 1) ? b2[k + 1] - b2[k] : 0.f;
+        const float u1y = ylast ? 0.f : n1[k] - b1[k];
+        const float u2y = ylast ? 0.f : n2[k] - b2[k];
+        nr[k] = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
+        big = fmaxf(big, nr[k]);
+        x11[k] = x11[k] + tau * u1x;
+        x12[k] = x12[k] + tau * u1y;
+        x21[k] = x21[k] + tau * u2x;
+        x22[k] = x22[k] + tau * u2y;
+    }
+    if (big > 1.f) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (nr[k] > 1.f) div4_shared(x11[k], x12[k], x21[k], x22[k], nr[k]);
+    }
+    *reinterpret_cast<float4 *>(S.xi(0, r) + cx) = make_float4(x11[0], x11[1], x11[2], x11[3]);
+    *reinterpret_cast<float4 *>(S.xi(1, r) + cx) = make_float4(x12[0], x12[1], x12[2], x12[3]);
+    *reinterpret_cast<float4 *>(S.xi(2, r) + cx) = make_float4(x21[0], x21[1], x21[2], x21[3]);
+    *reinterpret_cast<float4 *>(S.xi(3, r) + cx) = make_float4(x22[0], x22[1], x22[2], x22[3]);
+}
+
+// divergence, TH, primal step and extrapolation of one column quad of relative row r.
+// Returns max |du|^2 over the quad's pixels that are inside the frame.  Results go to o1,o2,ob1,ob2.
+__device__ __forceinline__ float t2_primal_quad(Tile2Smem &S, const TvArgs &a, int r, int qi, int gx0, int gy, int w, int hg,
+                                                float (&o1)[4], float (&o2)[4], float (&ob1)[4], float (&ob2)[4]) {
+    const int cx = 4 * qi;
+    const float tau = a.tau, l_t = a.l_t;
+    const float4 M11 = *reinterpret_cast<const float4 *>(S.xi(0, r) + cx);
+    const float4 M12 = *reinterpret_cast<const float4 *>(S.xi(1, r) + cx);
+    const float4 M21 = *reinterpret_cast<const float4 *>(S.xi(2, r) + cx);
+    const float4 M22 = *reinterpret_cast<const float4 *>(S.xi(3, r) + cx);
+    const float4 T12 = *reinterpret_cast<const float4 *>(S.xi(1, r - 1) + cx);
+    const float4 T22 = *reinterpret_cast<const float4 *>(S.xi(3, r - 1) + cx);
+    const float l11 = cx ? S.xi(0, r)[cx - 1] : 0.f, l21 = cx ? S.xi(2, r)[cx - 1] : 0.f;
+    const float4 U1 = *reinterpret_cast<const float4 *>(S.pl(0, r) + cx);
+    const float4 U2 = *reinterpret_cast<const float4 *>(S.pl(1, r) + cx);
+    const float4 C0 = *reinterpret_cast<const float4 *>(S.pl(2, r) + cx);
+    const float4 IX = *reinterpret_cast<const float4 *>(S.pl(3, r) + cx);
+    const float4 IY = *reinterpret_cast<const float4 *>(S.pl(4, r) + cx);
+    const float m11[4] = {M11.x, M11.y, M11.z, M11.w}, m12[4] = {M12.x, M12.y, M12.z, M12.w};
+    const float m21[4] = {M21.x, M21.y, M21.z, M21.w}, m22[4] = {M22.x, M22.y, M22.z, M22.w};
+    const float p12[4] = {T12.x, T12.y, T12.z, T12.w}, p22[4] = {T22.x, T22.y, T22.z, T22.w};
+    const float u1[4] = {U1.x, U1.y, U1.z, U1.w}, u2[4] = {U2.x, U2.y, U2.z, U2.w};
+    const float cc[4] = {C0.x, C0.y, C0.z, C0.w};
+    const float ix[4] = {IX.x, IX.y, IX.z, IX.w}, iy[4] = {IY.x, IY.y, IY.z, IY.w};
+    const bool interior = gx0 > 0 && gx0 + 4 < w && gy > 0 && gy < hg - 1;
+    float emax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int gx = gx0 + k;
+        float d1, d2;
+        if (interior) {
+            d1 = (m11[k] - (k ? m11[k - 1] : l11)) + (m12[k] - p12[k]);
+            d2 = (m21[k] - (k ? m21[k - 1] : l21)) + (m22[k] - p22[k]);
+        } else {
+            d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, gy, w, hg);
+            d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, gy, w, hg);
+        }
+        const float grad = ix[k] * ix[k] + iy[k] * iy[k];
+        const float rho = cc[k] + (ix[k] * u1[k] + iy[k] * u2[k]);
+        const float thr = l_t * grad;
+        float sc = -rho / grad;
+        sc = grad_is_zero(grad) ? 0.f : sc;
+        sc = (rho > thr) ? -l_t : sc;
+        sc = (rho < -l_t * grad) ? l_t : sc;
+        const float v1 = u1[k] + sc * ix[k];
+        const float v2 = u2[k] + sc * iy[k];
+        o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
+        o2[k] = u2[k] - tau * (-d2 + div_const(u2[k] - v2, a.dth));
+        const float e = (o1[k] - u1[k]) * (o1[k] - u1[k]) + (o2[k] - u2[k]) * (o2[k] - u2[k]);
+        if (gx >= 0 && gx < w) emax = fmaxf(emax, e);
+        ob1[k] = 2 * o1[k] - u1[k];
+        ob2[k] = 2 * o2[k] - u2[k];
+    }
+    return emax;
+}
+
+struct T2Args {
+    unsigned char *stat;  // [B][max_iters/2 + 2]: 1 = that launch ran both iterations normally
+    int stat_stride;
+};
+
+__global__ void __launch_bounds__(TT_THREADS, 3) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
+    extern __shared__ unsigned char smem_raw2[];
+    Tile2Smem &S = *reinterpret_cast<Tile2Smem *>(((size_t)smem_raw2 + 127) & ~(size_t)127);
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int par0 = a.parity[b];
+    const int it = 2 * L;  // first iteration of this launch
+
+    // ---- what does this launch do for pair b?  (see the header comment) ----
+    int mode, par_in = (par0 + L) & 1;
+    {
+        unsigned char *st = t2.stat + (size_t)b * t2.stat_stride;
+        if (L == 0) {
+            mode = (it + 1 < a.max_iters) ? T2_MODE_TWO : T2_MODE_ONE;
+        } else if (!st[L - 1]) {
+            mode = T2_MODE_SKIP;
+        } else {
+            const float e0 = __uint_as_float(a.err_chk[(size_t)b * a.max_iters + it - 2]);
+            const float e1 = __uint_as_float(a.err_chk[(size_t)b * a.max_iters + it - 1]);
+            if (!(e0 > a.tol2)) {
+                mode = T2_MODE_FIXUP;  // redo iteration it-2 alone, from the previous launch's input set
+                par_in ^= 1;
+            } else if (!(e1 > a.tol2) || it >= a.max_iters) {
+                mode = T2_MODE_SKIP;
+            } else {
+                mode = (it + 1 < a.max_iters) ? T2_MODE_TWO : T2_MODE_ONE;
+            }
+        }
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) st[L] = (mode == T2_MODE_TWO);
+    }
+    if (mode == T2_MODE_SKIP) return;
+
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch, hg = a.g.hg, yo = a.g.y_off;
+    const int x0 = blockIdx.x * TT_W, y0 = blockIdx.y * TT_H;
+    const int rows = min(TT_H, h - y0);
+    const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
+    float *out = a.state + (size_t)(par_in ^ 1) * a.set_stride + (size_t)b * plane;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"((unsigned)T2_TX_BYTES) : "memory");
+        const int B = a.g.B, zs = par_in * ST_COUNT * B + b;
+        tma_box(S.ub_[0], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB1 * B, &S.bar);
+        tma_box(S.ub_[1], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB2 * B, &S.bar);
+#pragma unroll
+        for (int k = 0; k < 4; k++) tma_box(S.xi_[k], &maps.xi, x0 - 4, y0 - 2, zs + (ST_XI11 + k) * B, &S.bar);
+        tma_box(S.pl_[0], &maps.pl, x0 - 4, y0 - 1, zs + ST_U1 * B, &S.bar);
+        tma_box(S.pl_[1], &maps.pl, x0 - 4, y0 - 1, zs + ST_U2 * B, &S.bar);
+        tma_box(S.pl_[2], &maps.c0, x0 - 4, y0 - 1, b, &S.bar);
+        tma_box(S.pl_[3], &maps.ix, x0 - 4, y0 - 1, b, &S.bar);
+        tma_box(S.pl_[4], &maps.iy, x0 - 4, y0 - 1, b, &S.bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(smem_u32(&S.bar)), "r"(0)
+                : "memory");
+        }
+    }
+    __syncthreads();
+
+    const float tau = a.tau;
+    float emaxA = 0.f, emaxB = 0.f;
+
+    if (mode == T2_MODE_TWO) {
+        // ---- 1A: xi_A on relative rows -2 .. rows (clipped to the frame), all 34 column quads ----
+        for (int t = tid; t < (TT_H + 3) * T2_QUADS; t += TT_THREADS) {
+            const int r = t / T2_QUADS - 2, qi = t % T2_QUADS;
+            const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
+            if (y < 0 || y >= h || gx0 + 3 < 0 || gx0 >= w) continue;
+            t2_dual_quad(S, r, qi, gx0, y + yo, w, hg, tau);
+        }
+        __syncthreads();
+        // ---- 2A: u_A, ubar_A in shared memory on relative rows -1 .. rows ----
+        for (int t = tid; t < (TT_H + 2) * T2_QUADS; t += TT_THREADS) {
+            const int r = t / T2_QUADS - 1, qi = t % T2_QUADS;
+            const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
+            if (y < 0 || y >= h || gx0 + 3 < 0 || gx0 >= w) continue;
+            float o1[4], o2[4], ob1[4], ob2[4];
+            const float e = t2_primal_quad(S, a, r, qi, gx0, y + yo, w, hg, o1, o2, ob1, ob2);
+            // the error of iteration A counts each pixel once: only the tile's own pixels
+            if (r >= 0 && r < rows && qi >= 1 && qi <= 32 && y >= a.g.own_lo && y < a.g.own_hi) emaxA = fmaxf(emaxA, e);
+            const int cx = 4 * qi;
+            *reinterpret_cast<float4 *>(S.pl(0, r) + cx) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<float4 *>(S.pl(1, r) + cx) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            *reinterpret_cast<float4 *>(S.ub(0, r) + cx) = make_float4(ob1[0], ob1[1], ob1[2], ob1[3]);
+            *reinterpret_cast<float4 *>(S.ub(1, r) + cx) = make_float4(ob2[0], ob2[1], ob2[2], ob2[3]);
+        }
+        __syncthreads();
+    }
+
+    // ---- 1B (or the only iteration): xi on relative rows -1 .. rows-1, column quads 0 .. 32 ----
+    for (int t = tid; t < (TT_H + 1) * 33; t += TT_THREADS) {
+        const int r = t / 33 - 1, qi = t % 33;
+        const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
+        if (y < 0 || r >= rows || gx0 + 3 < 0 || gx0 >= w) continue;
+        t2_dual_quad(S, r, qi, gx0, y + yo, w, hg, tau);
+    }
+    __syncthreads();
+    // ---- 2B: the tile itself, results to HBM ----
+    for (int t = tid; t < TT_H * 32; t += TT_THREADS) {
+        const int r = t >> 5, qi = (t & 31) + 1;
+        const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
+        if (r >= rows || gx0 >= pitch || y < a.g.own_lo || y >= a.g.own_hi) continue;
+        float o1[4], o2[4], ob1[4], ob2[4];
+        emaxB = fmaxf(emaxB, t2_primal_quad(S, a, r, qi, gx0, y + yo, w, hg, o1, o2, ob1, ob2));
+        const int cx = 4 * qi;
+        const size_t o = (size_t)y * pitch + gx0;
+        st4(out + ST_XI11 * ks + o, *reinterpret_cast<const float4 *>(S.xi(0, r) + cx));
+        st4(out + ST_XI12 * ks + o, *reinterpret_cast<const float4 *>(S.xi(1, r) + cx));
+        st4(out + ST_XI21 * ks + o, *reinterpret_cast<const float4 *>(S.xi(2, r) + cx));
+        st4(out + ST_XI22 * ks + o, *reinterpret_cast<const float4 *>(S.xi(3, r) + cx));
+        st4(out + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+        st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+        st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+    }
+
+    // ---- convergence measures: err(it) from 2A, err(it+1) from 2B; a fix-up records nothing ----
+    if (mode == T2_MODE_FIXUP) return;
+    const int lane = tid & 31, wid = tid >> 5;
+    emaxA = warp_max(emaxA);
+    emaxB = warp_max(emaxB);
+    if (lane == 0) {
+        S.red[0][wid] = emaxA;
+        S.red[1][wid] = emaxB;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float mA = S.red[0][0], mB = S.red[1][0];
+        for (int i = 1; i < TT_THREADS / 32; i++) {
+            mA = fmaxf(mA, S.red[0][i]);
+            mB = fmaxf(mB, S.red[1][i]);
+        }
+        unsigned *e = a.err_max + (size_t)b * a.max_iters + it;
+        if (mode == T2_MODE_TWO) {
+            atomicMax(e, __float_as_uint(mA));
+            atomicMax(e + 1, __float_as_uint(mB));
+        } else {
+            atomicMax(e, __float_as_uint(mB));
+        }
+    }
+}
+
+}  // namespace faldoi
