@@ -205,12 +205,12 @@ static int make_tile_maps(faldoi_solver *s) {
     if ((rc = make_plane_map(&s->maps.ix, s->Ix, g, g.B, TT_W, TT_H))) return rc;
     if ((rc = make_plane_map(&s->maps.iy, s->Iy, g, g.B, TT_W, TT_H))) return rc;
     if (!method_is_csad(s->method)) {  // boxes of the two-iteration kernel (2-pixel apron)
-        if ((rc = make_plane_map(&s->maps2.ub, s->state, g, nstate, TT_PW, T2_UB_ROWS))) return rc;
-        if ((rc = make_plane_map(&s->maps2.xi, s->state, g, nstate, TT_PW, T2_XI_ROWS))) return rc;
-        if ((rc = make_plane_map(&s->maps2.pl, s->state, g, nstate, TT_PW, T2_PL_ROWS))) return rc;
-        if ((rc = make_plane_map(&s->maps2.c0, c0, g, g.B, TT_PW, T2_PL_ROWS))) return rc;
-        if ((rc = make_plane_map(&s->maps2.ix, s->Ix, g, g.B, TT_PW, T2_PL_ROWS))) return rc;
-        if ((rc = make_plane_map(&s->maps2.iy, s->Iy, g, g.B, TT_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.ub, s->state, g, nstate, T2_PW, T2_UB_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.xi, s->state, g, nstate, T2_PW, T2_XI_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.pl, s->state, g, nstate, T2_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.c0, c0, g, g.B, T2_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.ix, s->Ix, g, g.B, T2_PW, T2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->maps2.iy, s->Iy, g, g.B, T2_PW, T2_PL_ROWS))) return rc;
     }
     return FALDOI_OK;
 }
@@ -600,7 +600,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             // two iterations per launch: ceil(max_iters/2) launches + one slot for a trailing fix-up
             const int nL = (p->max_iters + 1) / 2 + 1, LCHUNK = 13;
             FALDOI_CUDA(cudaMemsetAsync(s->t2_stat, 0, (size_t)g.B * s->t2_stride, s->stream));
-            const dim3 grid((g.pitch + TT_W - 1) / TT_W, (g.h + TT_H - 1) / TT_H, npairs);
+            const dim3 grid((g.pitch + T2_W - 1) / T2_W, (g.h + T2_H - 1) / T2_H, npairs);
             T2Args t2{s->t2_stat, s->t2_stride};
             for (int c = 0, L = 0; L < nL; c++) {
                 if (c >= 2) {
@@ -609,7 +609,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
                 }
                 const int end = (L + LCHUNK < nL) ? L + LCHUNK : nL;
                 for (; L < end; L++) {
-                    tv_tile2_kernel<<<grid, TT_THREADS, sizeof(Tile2Smem) + 128, s->stream>>>(s->maps2, a, t2, L);
+                    tv_tile2_kernel<<<grid, T2_THREADS, sizeof(Tile2Smem) + 128, s->stream>>>(s->maps2, a, t2, L);
                     s->launches++;
                 }
                 const int Lc = (L - 1 < (p->max_iters + 1) / 2) ? L - 1 : (p->max_iters + 1) / 2 - 1;

@@ -1,11 +1,11 @@
 // Temporally blocked TVL2 iteration: TWO primal-dual iterations per pass over HBM.
 //
 // Same arithmetic as tv_tile_kernel<DATA_TVL1> (see tv_kernels.cuh for the reference citations),
-// but a CTA stages its 128x8 tile with a 2-pixel apron, runs iteration A on the apron-extended
+// but a CTA stages its 120x8 tile with a 2-row / 4-column apron, runs iteration A on the apron-extended
 // region entirely in shared memory, then iteration B on the tile, and writes the 8 state planes
 // once: 41 instead of 76 bytes of HBM traffic per pixel and iteration for 14 % more arithmetic.
 //
-//   staged (TMA boxes, cols x0-4 .. x0+131):   ubar  rows y0-2 .. y0+9
+//   staged (TMA boxes, cols x0-4 .. x0+123):   ubar  rows y0-2 .. y0+9
 //                                              xi    rows y0-2 .. y0+8
 //                                              u, rho_c, Ix, Iy   rows y0-1 .. y0+8
 //   1A  xi_A   rows y0-2 .. y0+8      2A  u_A, ubar_A (in smem)  rows y0-1 .. y0+8, err(2L) over the tile
@@ -22,31 +22,40 @@
 
 namespace faldoi {
 
+// Geometry: the staged region is 128 columns (32 float4 quads, x0-4 .. x0+123) so that ONE WARP
+// owns one staged row and a lane owns one quad -- no index arithmetic, row tests are warp-uniform,
+// and every phase is a single balanced round: 11 / 10 / 9 / 8 busy warps of the CTA's 11.  The tile
+// written back is the inner 120 x 8 pixels (quads 1..30).
 enum {
-    T2_UB_ROWS = TT_H + 4,
-    T2_XI_ROWS = TT_H + 3,
-    T2_PL_ROWS = TT_H + 2,
-    T2_UB_FLOATS = (T2_UB_ROWS * TT_PW + 31) / 32 * 32,
-    T2_XI_FLOATS = (T2_XI_ROWS * TT_PW + 31) / 32 * 32,
-    T2_PL_FLOATS = (T2_PL_ROWS * TT_PW + 31) / 32 * 32,
-    T2_TX_BYTES = (2 * T2_UB_ROWS + 4 * T2_XI_ROWS + 5 * T2_PL_ROWS) * TT_PW * 4,
-    T2_QUADS = TT_PW / 4  // 34 column quads: smem columns 0..135 <-> x0-4 .. x0+131
+    T2_H = 8,                 // tile rows
+    T2_W = 120,               // tile columns written by a CTA
+    T2_PW = 128,              // staged columns
+    T2_QUADS = T2_PW / 4,     // 32
+    T2_WARPS = T2_H + 3,      // one per staged xi row
+    T2_THREADS = 32 * T2_WARPS,
+    T2_UB_ROWS = T2_H + 4,
+    T2_XI_ROWS = T2_H + 3,
+    T2_PL_ROWS = T2_H + 2,
+    T2_UB_FLOATS = T2_UB_ROWS * T2_PW,
+    T2_XI_FLOATS = T2_XI_ROWS * T2_PW,
+    T2_PL_FLOATS = T2_PL_ROWS * T2_PW,
+    T2_TX_BYTES = (2 * T2_UB_ROWS + 4 * T2_XI_ROWS + 5 * T2_PL_ROWS) * T2_PW * 4
 };
 
 struct Tile2Smem {
     float ub_[2][T2_UB_FLOATS];  // row index = relative row + 2
     float xi_[4][T2_XI_FLOATS];  // row index = relative row + 2
     float pl_[5][T2_PL_FLOATS];  // u1, u2, rho_c, Ix, Iy; row index = relative row + 1
-    float red[2][TT_THREADS / 32];
+    float red[2][T2_WARPS];
     unsigned long long bar;
-    __device__ __forceinline__ float *ub(int k, int r) { return &ub_[k][(r + 2) * TT_PW]; }
-    __device__ __forceinline__ float *xi(int k, int r) { return &xi_[k][(r + 2) * TT_PW]; }
-    __device__ __forceinline__ float *pl(int k, int r) { return &pl_[k][(r + 1) * TT_PW]; }
+    __device__ __forceinline__ float *ub(int k, int r) { return &ub_[k][(r + 2) * T2_PW]; }
+    __device__ __forceinline__ float *xi(int k, int r) { return &xi_[k][(r + 2) * T2_PW]; }
+    __device__ __forceinline__ float *pl(int k, int r) { return &pl_[k][(r + 1) * T2_PW]; }
 };
 
 struct Tile2Maps {
-    CUtensorMap ub, xi, pl;  // state array, boxes 136 x {12, 11, 10}
-    CUtensorMap c0, ix, iy;  // rho_c, Ix, Iy: box 136 x 10
+    CUtensorMap ub, xi, pl;  // state array, boxes 128 x {12, 11, 10}
+    CUtensorMap c0, ix, iy;  // rho_c, Ix, Iy: box 128 x 10
 };
 
 enum { T2_MODE_SKIP = 0, T2_MODE_TWO = 1, T2_MODE_ONE = 2, T2_MODE_FIXUP = 3 };
@@ -57,7 +66,7 @@ __device__ __forceinline__ void t2_dual_quad(Tile2Smem &S, int r, int qi, int gx
     const bool ylast = (gy == hg - 1);
     const float4 B1 = *reinterpret_cast<const float4 *>(S.ub(0, r) + cx);
     const float4 B2 = *reinterpret_cast<const float4 *>(S.ub(1, r) + cx);
-    const bool has_r = (cx + 4 < TT_PW);  // the last quad of the staged row has no right neighbour in smem (its value is never needed)
+    const bool has_r = (cx + 4 < T2_PW);  // the last quad of the staged row has no right neighbour in smem (its value is never needed)
     const float b1[5] = {B1.x, B1.y, B1.z, B1.w, has_r ? S.ub(0, r)[cx + 4] : 0.f};
     const float b2[5] = {B2.x, B2.y, B2.z, B2.w, has_r ? S.ub(1, r)[cx + 4] : 0.f};
     float4 N1 = make_float4(0.f, 0.f, 0.f, 0.f), N2 = N1;
@@ -160,11 +169,12 @@ struct T2Args {
     int stat_stride;
 };
 
-__global__ void __launch_bounds__(TT_THREADS, 3) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
-    extern __shared__ unsigned char smem_raw2[];
-    Tile2Smem &S = *reinterpret_cast<Tile2Smem *>(((size_t)smem_raw2 + 127) & ~(size_t)127);
+__global__ void __launch_bounds__(T2_THREADS, 3) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
+    // (no pointer arithmetic on the base: it would demote every access from LDS/STS to generic LD/ST)
+    extern __shared__ __align__(1024) unsigned char smem_raw2[];
+    Tile2Smem &S = *reinterpret_cast<Tile2Smem *>(smem_raw2);
     const int b = blockIdx.z;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
     const int par0 = a.parity[b];
     const int it = 2 * L;  // first iteration of this launch
 
@@ -193,8 +203,8 @@ __global__ void __launch_bounds__(TT_THREADS, 3) tv_tile2_kernel(const __grid_co
     if (mode == T2_MODE_SKIP) return;
 
     const int w = a.g.w, h = a.g.h, pitch = a.g.pitch, hg = a.g.hg, yo = a.g.y_off;
-    const int x0 = blockIdx.x * TT_W, y0 = blockIdx.y * TT_H;
-    const int rows = min(TT_H, h - y0);
+    const int x0 = blockIdx.x * T2_W, y0 = blockIdx.y * T2_H;
+    const int rows = min(T2_H, h - y0);
     const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
     float *out = a.state + (size_t)(par_in ^ 1) * a.set_stride + (size_t)b * plane;
 
@@ -226,75 +236,72 @@ __global__ void __launch_bounds__(TT_THREADS, 3) tv_tile2_kernel(const __grid_co
     __syncthreads();
 
     const float tau = a.tau;
+    const int qi = lane, gx0 = x0 - 4 + 4 * lane;       // this lane's column quad
+    const bool col_ok = (gx0 + 3 >= 0 && gx0 < w);      // some pixel of the quad is inside the frame
     float emaxA = 0.f, emaxB = 0.f;
 
     if (mode == T2_MODE_TWO) {
-        // ---- 1A: xi_A on relative rows -2 .. rows (clipped to the frame), all 34 column quads ----
-        for (int t = tid; t < (TT_H + 3) * T2_QUADS; t += TT_THREADS) {
-            const int r = t / T2_QUADS - 2, qi = t % T2_QUADS;
-            const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
-            if (y < 0 || y >= h || gx0 + 3 < 0 || gx0 >= w) continue;
-            t2_dual_quad(S, r, qi, gx0, y + yo, w, hg, tau);
+        // ---- 1A: xi_A, warp wi <-> relative row wi-2 (rows -2 .. T2_H) ----
+        {
+            const int r = wi - 2, y = y0 + r;
+            if (y >= 0 && y < h && col_ok) t2_dual_quad(S, r, qi, gx0, y + yo, w, hg, tau);
         }
         __syncthreads();
-        // ---- 2A: u_A, ubar_A in shared memory on relative rows -1 .. rows ----
-        for (int t = tid; t < (TT_H + 2) * T2_QUADS; t += TT_THREADS) {
-            const int r = t / T2_QUADS - 1, qi = t % T2_QUADS;
-            const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
-            if (y < 0 || y >= h || gx0 + 3 < 0 || gx0 >= w) continue;
-            float o1[4], o2[4], ob1[4], ob2[4];
-            const float e = t2_primal_quad(S, a, r, qi, gx0, y + yo, w, hg, o1, o2, ob1, ob2);
-            // the error of iteration A counts each pixel once: only the tile's own pixels
-            if (r >= 0 && r < rows && qi >= 1 && qi <= 32 && y >= a.g.own_lo && y < a.g.own_hi) emaxA = fmaxf(emaxA, e);
-            const int cx = 4 * qi;
-            *reinterpret_cast<float4 *>(S.pl(0, r) + cx) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-            *reinterpret_cast<float4 *>(S.pl(1, r) + cx) = make_float4(o2[0], o2[1], o2[2], o2[3]);
-            *reinterpret_cast<float4 *>(S.ub(0, r) + cx) = make_float4(ob1[0], ob1[1], ob1[2], ob1[3]);
-            *reinterpret_cast<float4 *>(S.ub(1, r) + cx) = make_float4(ob2[0], ob2[1], ob2[2], ob2[3]);
+        // ---- 2A: u_A, ubar_A in shared memory, warp wi <-> relative row wi-1 (rows -1 .. T2_H) ----
+        if (wi < T2_H + 2) {
+            const int r = wi - 1, y = y0 + r;
+            if (y >= 0 && y < h && col_ok) {
+                float o1[4], o2[4], ob1[4], ob2[4];
+                const float e = t2_primal_quad(S, a, r, qi, gx0, y + yo, w, hg, o1, o2, ob1, ob2);
+                // the error of iteration A counts each pixel once: only the tile's own pixels
+                if (r >= 0 && r < rows && qi >= 1 && qi <= T2_W / 4 && y >= a.g.own_lo && y < a.g.own_hi) emaxA = e;
+                const int cx = 4 * qi;
+                *reinterpret_cast<float4 *>(S.pl(0, r) + cx) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<float4 *>(S.pl(1, r) + cx) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+                *reinterpret_cast<float4 *>(S.ub(0, r) + cx) = make_float4(ob1[0], ob1[1], ob1[2], ob1[3]);
+                *reinterpret_cast<float4 *>(S.ub(1, r) + cx) = make_float4(ob2[0], ob2[1], ob2[2], ob2[3]);
+            }
         }
         __syncthreads();
     }
 
-    // ---- 1B (or the only iteration): xi on relative rows -1 .. rows-1, column quads 0 .. 32 ----
-    for (int t = tid; t < (TT_H + 1) * 33; t += TT_THREADS) {
-        const int r = t / 33 - 1, qi = t % 33;
-        const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
-        if (y < 0 || r >= rows || gx0 + 3 < 0 || gx0 >= w) continue;
-        t2_dual_quad(S, r, qi, gx0, y + yo, w, hg, tau);
+    // ---- 1B (or the only iteration): xi, warp wi <-> relative row wi-1 (rows -1 .. rows-1), quads 0 .. 30 ----
+    if (wi < T2_H + 1) {
+        const int r = wi - 1, y = y0 + r;
+        if (y >= 0 && r < rows && col_ok && qi <= T2_W / 4) t2_dual_quad(S, r, qi, gx0, y + yo, w, hg, tau);
     }
     __syncthreads();
-    // ---- 2B: the tile itself, results to HBM ----
-    for (int t = tid; t < TT_H * 32; t += TT_THREADS) {
-        const int r = t >> 5, qi = (t & 31) + 1;
-        const int y = y0 + r, gx0 = x0 - 4 + 4 * qi;
-        if (r >= rows || gx0 >= pitch || y < a.g.own_lo || y >= a.g.own_hi) continue;
-        float o1[4], o2[4], ob1[4], ob2[4];
-        emaxB = fmaxf(emaxB, t2_primal_quad(S, a, r, qi, gx0, y + yo, w, hg, o1, o2, ob1, ob2));
-        const int cx = 4 * qi;
-        const size_t o = (size_t)y * pitch + gx0;
-        st4(out + ST_XI11 * ks + o, *reinterpret_cast<const float4 *>(S.xi(0, r) + cx));
-        st4(out + ST_XI12 * ks + o, *reinterpret_cast<const float4 *>(S.xi(1, r) + cx));
-        st4(out + ST_XI21 * ks + o, *reinterpret_cast<const float4 *>(S.xi(2, r) + cx));
-        st4(out + ST_XI22 * ks + o, *reinterpret_cast<const float4 *>(S.xi(3, r) + cx));
-        st4(out + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
-        st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
-        st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
-        st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+    // ---- 2B: the tile itself (warp wi <-> row wi, quads 1 .. 30), results to HBM ----
+    if (wi < T2_H) {
+        const int r = wi, y = y0 + r;
+        if (r < rows && qi >= 1 && qi <= T2_W / 4 && gx0 < pitch && y >= a.g.own_lo && y < a.g.own_hi) {
+            float o1[4], o2[4], ob1[4], ob2[4];
+            emaxB = t2_primal_quad(S, a, r, qi, gx0, y + yo, w, hg, o1, o2, ob1, ob2);
+            const int cx = 4 * qi;
+            const size_t o = (size_t)y * pitch + gx0;
+            st4(out + ST_XI11 * ks + o, *reinterpret_cast<const float4 *>(S.xi(0, r) + cx));
+            st4(out + ST_XI12 * ks + o, *reinterpret_cast<const float4 *>(S.xi(1, r) + cx));
+            st4(out + ST_XI21 * ks + o, *reinterpret_cast<const float4 *>(S.xi(2, r) + cx));
+            st4(out + ST_XI22 * ks + o, *reinterpret_cast<const float4 *>(S.xi(3, r) + cx));
+            st4(out + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+            st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+            st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+        }
     }
 
     // ---- convergence measures: err(it) from 2A, err(it+1) from 2B; a fix-up records nothing ----
     if (mode == T2_MODE_FIXUP) return;
-    const int lane = tid & 31, wid = tid >> 5;
     emaxA = warp_max(emaxA);
     emaxB = warp_max(emaxB);
     if (lane == 0) {
-        S.red[0][wid] = emaxA;
-        S.red[1][wid] = emaxB;
+        S.red[0][wi] = emaxA;
+        S.red[1][wi] = emaxB;
     }
     __syncthreads();
     if (tid == 0) {
         float mA = S.red[0][0], mB = S.red[1][0];
-        for (int i = 1; i < TT_THREADS / 32; i++) {
+        for (int i = 1; i < T2_WARPS; i++) {
             mA = fmaxf(mA, S.red[0][i]);
             mB = fmaxf(mB, S.red[1][i]);
         }

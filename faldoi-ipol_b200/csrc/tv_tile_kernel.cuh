@@ -79,8 +79,9 @@ __device__ __forceinline__ void tma_box(void *dst_smem, const CUtensorMap *map, 
 
 template <int DATA>
 __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS_CSAD : FALDOI_TT_CTAS) tv_tile_kernel(const __grid_constant__ TileMaps maps, TvArgs a, int it) {
-    extern __shared__ unsigned char smem_raw[];
-    TileSmem &S = *reinterpret_cast<TileSmem *>(((size_t)smem_raw + 127) & ~(size_t)127);
+    // (no pointer arithmetic on the base: it would demote every access from LDS/STS to generic LD/ST)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
     const int b = blockIdx.z;
     const int par0 = a.parity[b];  // issued together with the error word read by pair_active: one L2 round trip
     if (!pair_active<DATA>(a, b, it)) return;
