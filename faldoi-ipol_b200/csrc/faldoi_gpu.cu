@@ -789,6 +789,12 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
         const char *e = getenv("FALDOI_OCC_FUSED");  // "0" selects the one-sweep-per-launch kernels
         return !(e && e[0] == '0');
     }();
+    static const bool rows_variant = [] {
+        const char *e = getenv("FALDOI_OCC_FUSED");  // "smem" selects the shared-memory-resident fused kernels
+        return !(e && strcmp(e, "smem") == 0);
+    }();
+    static_assert(OCC_NS <= 4, "the register-resident OCC kernels stage a 4-column apron");
+    const dim3 rgrd((g.pitch + OR_W - 1) / OR_W, (g.h + OR_TH - 1) / OR_TH, npairs);
     OccArgs a{};
     a.pl = s->occ;
     a.I0 = s->I0;
@@ -819,14 +825,23 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
         for (int it = 0; it < p->max_iters; it++) {
             occ_v_kernel<<<grd, blk, 0, s->stream>>>(a, it);
             if (fused) {
-                for (int k = 0; k < 24 / OCC_NS; k++) occ_xi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1);
+                for (int k = 0; k < 24 / OCC_NS; k++) {
+                    if (rows_variant)
+                        occ_xi_rows_kernel<OCC_NS><<<rgrd, 32 * (OR_TH + 2 * OCC_NS), 0, s->stream>>>(a, it, k & 1);
+                    else
+                        occ_xi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1);
+                }
             } else {
                 for (int k = 0; k < 24; k++) occ_xi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1);
             }
             occ_u_kernel<<<grd, blk, 0, s->stream>>>(a, it);
             if (fused) {
-                for (int k = 0; k < 24 / OCC_NS; k++)
-                    occ_chi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
+                for (int k = 0; k < 24 / OCC_NS; k++) {
+                    if (rows_variant)
+                        occ_chi_rows_kernel<OCC_NS><<<rgrd, 32 * (OR_TH + 2 * OCC_NS), 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
+                    else
+                        occ_chi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
+                }
                 s->launches += 2 + 2 * (24 / OCC_NS);
             } else {
                 for (int k = 0; k < 24; k++) occ_chi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1, k == 23);

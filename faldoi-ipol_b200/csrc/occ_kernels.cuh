@@ -499,6 +499,195 @@ __global__ void __launch_bounds__(256) occ_chi_multi_kernel(OccArgs a, int it, i
     }
 }
 
+// ---------------------------------------------------------------------------
+// Register-resident variant of the temporally blocked sweeps (the default).
+// One WARP owns one staged row, one LANE one float4 quad of it, for all NS sweeps: the
+// lane's own xi / eta / chi and the constants g, v, k (F, G) live in registers; only what a
+// neighbour needs crosses lanes -- left / right neighbours by warp shuffle, the rows above /
+// below through two shared-memory planes.  Staged region: 128 columns (x0-4 .. x0+123) by
+// OR_TH + 2 NS rows; written back: the inner 120 x OR_TH pixels.  NS <= 4 (the column apron).
+// ---------------------------------------------------------------------------
+#ifndef FALDOI_OCC_TH
+#define FALDOI_OCC_TH 16
+#endif
+enum { OR_TH = FALDOI_OCC_TH, OR_W = 120, OR_PW = 128 };
+
+__device__ __forceinline__ void q2a(const float4 &q, float (&x)[4]) { x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w; }
+__device__ __forceinline__ float4 a2q(const float (&x)[4]) { return make_float4(x[0], x[1], x[2], x[3]); }
+
+template <int NS>
+__global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_xi_rows_kernel(OccArgs a, int it, int src) {
+    constexpr int ROWS = OR_TH + 2 * NS;
+    __shared__ __align__(16) float sB[2][ROWS][OR_PW];  // g*xi12, g*xi22 of every staged row (for the row below)
+    __shared__ __align__(16) float sV[2][ROWS][OR_PW];  // vi1, vi2 (for the row above)
+    const int b = blockIdx.z;
+    if (!occ_active(a, b, it)) return;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * OR_W, y0 = blockIdx.y * OR_TH;
+    const int gx0 = x0 - 4 + 4 * lane, gy = y0 - NS + r;
+    const int cx = 4 * lane;
+    const size_t ks = (size_t)a.g.B * a.g.plane;
+    const float theta = a.theta, tt = a.tau_theta;
+    const bool in = gy >= 0 && gy < h && gx0 >= 0 && gx0 < pitch;
+    const size_t p = (size_t)gy * pitch + gx0;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *xin = occ_plane(a, src ? OC_XI1 : OC_XI0, b);
+    float x11[4], x12[4], x21[4], x22[4], g[4], v1[4], v2[4], k1[4], k2[4];
+    q2a(in ? ld4(xin + p) : z4, x11);
+    q2a(in ? ld4(xin + ks + p) : z4, x12);
+    q2a(in ? ld4(xin + 2 * ks + p) : z4, x21);
+    q2a(in ? ld4(xin + 3 * ks + p) : z4, x22);
+    q2a(in ? ld4(occ_plane(a, OC_G, b) + p) : z4, g);
+    q2a(in ? ld4(occ_plane(a, OC_V1, b) + p) : z4, v1);
+    q2a(in ? ld4(occ_plane(a, OC_V2, b) + p) : z4, v2);
+    q2a(in ? ld4(occ_plane(a, OC_K1, b) + p) : z4, k1);
+    q2a(in ? ld4(occ_plane(a, OC_K2, b) + p) : z4, k2);
+
+#pragma unroll 1
+    for (int s = 0; s < NS; s++) {
+        float a1[4], b1[4], a2[4], b2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            a1[k] = g[k] * x11[k];
+            b1[k] = g[k] * x12[k];
+            a2[k] = g[k] * x21[k];
+            b2[k] = g[k] * x22[k];
+        }
+        *reinterpret_cast<float4 *>(&sB[0][r][cx]) = a2q(b1);
+        *reinterpret_cast<float4 *>(&sB[1][r][cx]) = a2q(b2);
+        __syncthreads();
+        float ub1[4], ub2[4];
+        q2a(r > 0 ? *reinterpret_cast<const float4 *>(&sB[0][r - 1][cx]) : z4, ub1);
+        q2a(r > 0 ? *reinterpret_cast<const float4 *>(&sB[1][r - 1][cx]) : z4, ub2);
+        const float la1 = __shfl_up_sync(0xffffffffu, a1[3], 1), la2 = __shfl_up_sync(0xffffffffu, a2[3], 1);
+        float vi1[4], vi2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = gx0 + k;
+            vi1[k] = v1[k] + theta * div_bc(a1[k], k ? a1[k - 1] : la1, b1[k], ub1[k], gx, gy, w, h) + k1[k];
+            vi2[k] = v2[k] + theta * div_bc(a2[k], k ? a2[k - 1] : la2, b2[k], ub2[k], gx, gy, w, h) + k2[k];
+        }
+        *reinterpret_cast<float4 *>(&sV[0][r][cx]) = a2q(vi1);
+        *reinterpret_cast<float4 *>(&sV[1][r][cx]) = a2q(vi2);
+        __syncthreads();
+        float dn1[4], dn2[4];
+        q2a(r < ROWS - 1 ? *reinterpret_cast<const float4 *>(&sV[0][r + 1][cx]) : z4, dn1);
+        q2a(r < ROWS - 1 ? *reinterpret_cast<const float4 *>(&sV[1][r + 1][cx]) : z4, dn2);
+        const float rv1 = __shfl_down_sync(0xffffffffu, vi1[0], 1), rv2 = __shfl_down_sync(0xffffffffu, vi2[0], 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = gx0 + k;
+            {
+                const float gxv = (gx < w - 1) ? (k < 3 ? vi1[k + 1] : rv1) - vi1[k] : 0.f;
+                const float gyv = (gy < h - 1) ? dn1[k] - vi1[k] : 0.f;
+                const float e1 = g[k] * gxv, e2 = g[k] * gyv;
+                const float nrm = sqrtf(e1 * e1 + e2 * e2);
+                float q1 = x11[k] + tt * e1, q2 = x12[k] + tt * e2;
+                div2_shared(q1, q2, 1 + tt * nrm);
+                x11[k] = q1;
+                x12[k] = q2;
+            }
+            {
+                const float gxv = (gx < w - 1) ? (k < 3 ? vi2[k + 1] : rv2) - vi2[k] : 0.f;
+                const float gyv = (gy < h - 1) ? dn2[k] - vi2[k] : 0.f;
+                const float e1 = g[k] * gxv, e2 = g[k] * gyv;
+                const float nrm = sqrtf(e1 * e1 + e2 * e2);
+                float q1 = x21[k] + tt * e1, q2 = x22[k] + tt * e2;
+                div2_shared(q1, q2, 1 + tt * nrm);
+                x21[k] = q1;
+                x22[k] = q2;
+            }
+        }
+    }
+    if (in && r >= NS && r < NS + OR_TH && lane >= 1 && lane <= OR_W / 4) {
+        float *xout = occ_plane(a, src ? OC_XI0 : OC_XI1, b);
+        st4(xout + p, a2q(x11));
+        st4(xout + ks + p, a2q(x12));
+        st4(xout + 2 * ks + p, a2q(x21));
+        st4(xout + 3 * ks + p, a2q(x22));
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_chi_rows_kernel(OccArgs a, int it, int src, int last) {
+    constexpr int ROWS = OR_TH + 2 * NS;
+    __shared__ __align__(16) float sC[ROWS][OR_PW];  // chi of every staged row (for the row above)
+    __shared__ __align__(16) float sE[ROWS][OR_PW];  // g*eta2 (for the row below)
+    const int b = blockIdx.z;
+    if (!occ_active(a, b, it)) return;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * OR_W, y0 = blockIdx.y * OR_TH;
+    const int gx0 = x0 - 4 + 4 * lane, gy = y0 - NS + r;
+    const int cx = 4 * lane;
+    const size_t ks = (size_t)a.g.B * a.g.plane;
+    const float mte = a.mu * a.tau_eta;
+    const bool in = gy >= 0 && gy < h && gx0 >= 0 && gx0 < pitch;
+    const size_t p = (size_t)gy * pitch + gx0;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *e_in = occ_plane(a, src ? OC_ETA1 : OC_ETA0, b);
+    float e1[4], e2[4], c[4], g[4], F[4], G[4];
+    q2a(in ? ld4(e_in + p) : z4, e1);
+    q2a(in ? ld4(e_in + ks + p) : z4, e2);
+    q2a(in ? ld4(occ_plane(a, src ? OC_CHI1 : OC_CHI0, b) + p) : z4, c);
+    q2a(in ? ld4(occ_plane(a, OC_G, b) + p) : z4, g);
+    q2a(in ? ld4(occ_plane(a, OC_F, b) + p) : z4, F);
+    q2a(in ? ld4(occ_plane(a, OC_GG, b) + p) : z4, G);
+
+#pragma unroll 1
+    for (int s = 0; s < NS; s++) {
+        *reinterpret_cast<float4 *>(&sC[r][cx]) = a2q(c);
+        __syncthreads();
+        float dn[4];
+        q2a(r < ROWS - 1 ? *reinterpret_cast<const float4 *>(&sC[r + 1][cx]) : z4, dn);
+        const float rc = __shfl_down_sync(0xffffffffu, c[0], 1);
+        float ge1[4], ge2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = gx0 + k;
+            const float chix = (gx < w - 1) ? (k < 3 ? c[k + 1] : rc) - c[k] : 0.f;
+            const float chiy = (gy < h - 1) ? dn[k] - c[k] : 0.f;
+            const float n1 = e1[k] + mte * g[k] * chix;
+            const float n2 = e2[k] + mte * g[k] * chiy;
+            const float ne = sqrtf(n1 * n1 + n2 * n2);
+            if (ne <= 1) {
+                e1[k] = n1;
+                e2[k] = n2;
+            } else {
+                e1[k] = n1 / ne;
+                e2[k] = n2 / ne;
+            }
+            ge1[k] = g[k] * e1[k];
+            ge2[k] = g[k] * e2[k];
+        }
+        *reinterpret_cast<float4 *>(&sE[r][cx]) = a2q(ge2);
+        __syncthreads();
+        float up[4];
+        q2a(r > 0 ? *reinterpret_cast<const float4 *>(&sE[r - 1][cx]) : z4, up);
+        const float le = __shfl_up_sync(0xffffffffu, ge1[3], 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gx = gx0 + k;
+            const float dge = div_bc(ge1[k], k ? ge1[k - 1] : le, ge2[k], up[k], gx, gy, w, h);
+            const float div_u = 0.f;  // target definition
+            const float cn = c[k] + a.tau_chi * (a.mu * dge - a.beta * div_u - F[k] - G[k]);
+            const float lo = (cn < 1) ? cn : 1;
+            c[k] = (lo > 0) ? lo : 0;
+        }
+    }
+    if (in && r >= NS && r < NS + OR_TH && lane >= 1 && lane <= OR_W / 4) {
+        float *e_out = occ_plane(a, src ? OC_ETA0 : OC_ETA1, b);
+        st4(e_out + p, a2q(e1));
+        st4(e_out + ks + p, a2q(e2));
+        if (last) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) c[k] = ((double)c[k] > 0.6) ? 1.f : 0.f;
+        }
+        st4(occ_plane(a, src ? OC_CHI0 : OC_CHI1, b) + p, a2q(c));
+    }
+}
+
 __global__ void occ_export_kernel(OccArgs a, float *packed) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
