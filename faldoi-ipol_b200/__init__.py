@@ -50,7 +50,8 @@ EXPORTS = [
     "faldoi_nltvl1_PD", "faldoi_nltvcsad_PD", "faldoi_guided_tvl2coupled_occ", "faldoi_centered_gradient",
     "faldoi_bicubic_warp", "faldoi_stripe_rows", "faldoi_stripes_create", "faldoi_stripes_destroy",
     "faldoi_stripes_upload", "faldoi_stripes_run", "faldoi_stripes_download", "faldoi_stripes_last_run_ms",
-    "faldoi_stripes_last_launches", "faldoi_selftest_division",
+    "faldoi_stripes_last_launches", "faldoi_selftest_division", "faldoi_solver_upload_raw",
+    "faldoi_solver_download_frames", "faldoi_global_solve_raw",
 ]
 
 
@@ -100,6 +101,9 @@ def lib():
         L.faldoi_stripes_last_launches.argtypes = [vp]
         L.faldoi_stripes_last_launches.restype = C.c_longlong
         L.faldoi_selftest_division.argtypes = [i, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+        L.faldoi_solver_upload_raw.argtypes = [vp, i, vp, vp, vp, i, vp, vp]
+        L.faldoi_solver_download_frames.argtypes = [vp, i, vp, vp, vp, vp]
+        L.faldoi_global_solve_raw.argtypes = [i, C.POINTER(Params), i, i, i, vp, vp, vp, vp, vp, C.POINTER(Log)]
         _lib = L
     return _lib
 
@@ -158,6 +162,21 @@ class Solver:
         arrs = [_f32(x) for x in (I0, I1, Im1, lab, u, chi)]
         _check(lib().faldoi_solver_upload(self._h, slot, *[_ptr(x) for x in arrs]))
         _check(lib().faldoi_solver_sync(self._h))  # host arrays may be temporaries
+
+    def upload_raw(self, slot, i0, i1, im1, u, chi=None):
+        """Raw planar frames (pd,h,w) 0..255; preprocessing runs on the device (faldoi_solver_upload_raw)."""
+        arrs = [_f32(x) for x in (i0, i1, im1, u, chi)]
+        _check(lib().faldoi_solver_upload_raw(self._h, slot, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), arrs[0].shape[0],
+                                              _ptr(arrs[3]), _ptr(arrs[4])))
+        _check(lib().faldoi_solver_sync(self._h))
+
+    def download_frames(self, slot):
+        """(I0n, I1n, Im1n or None, lab or None) as preprocessed on the device."""
+        I0n, I1n = np.empty((self.h, self.w), np.float32), np.empty((self.h, self.w), np.float32)
+        Im1n = np.empty((self.h, self.w), np.float32) if self.method == M_TVL1_OCC else None
+        lab = np.empty((3, self.h, self.w), np.float32) if self.method in (2, 3, 6, 7) else None
+        _check(lib().faldoi_solver_download_frames(self._h, slot, _ptr(I0n), _ptr(I1n), _ptr(Im1n), _ptr(lab)))
+        return I0n, I1n, Im1n, lab
 
     def upload_ptrs(self, slot, I0, I1, u, Im1=0, lab=0, chi=0):
         """Raw host pointers (e.g. pinned torch tensors' data_ptr()); asynchronous."""
@@ -261,6 +280,18 @@ def global_solve(method, I0, I1, u, Im1=None, lab=None, chi=None, params=None, w
     log = Log()
     arrs = [_f32(I0), _f32(I1), _f32(Im1), _f32(lab)]
     _check(lib().faldoi_global_solve(device, C.byref(p), w, h, *[_ptr(x) for x in arrs], _ptr(u), _ptr(chi_a), C.byref(log)))
+    return u, chi_a, list(log.iters[:p.warps]), list(log.err[:p.warps])
+
+
+def global_solve_raw(method, i0, i1, im1, u, chi=None, params=None, warps=5, glb_iters=400, device=0):
+    """global_faldoi from raw planar frames (pd,h,w) 0..255: preprocessing + solve on the device."""
+    pd, h, w = i0.shape
+    p = params or default_params(method, glb_iters, warps)
+    u = _f32(u).copy()
+    chi_a = _f32(chi).copy() if chi is not None else None
+    log = Log()
+    arrs = [_f32(i0), _f32(i1), _f32(im1)]
+    _check(lib().faldoi_global_solve_raw(device, C.byref(p), w, h, pd, *[_ptr(x) for x in arrs], _ptr(u), _ptr(chi_a), C.byref(log)))
     return u, chi_a, list(log.iters[:p.warps]), list(log.err[:p.warps])
 
 

@@ -13,6 +13,7 @@
 #include "warp_kernels.cuh"
 #include "nltv_kernels.cuh"
 #include "occ_kernels.cuh"
+#include "preprocess_kernels.cuh"
 
 using namespace faldoi;
 
@@ -20,6 +21,7 @@ static int occ_upload(faldoi_solver *s, int slot, const float *Im1, const float 
 static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs);
 static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs);
 static int up2d(faldoi_solver *s, float *dst_plane, const float *src);
+static dim3 grid2d(const Geo &g, dim3 block, int npairs);
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -379,6 +381,120 @@ extern "C" int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0,
     if (fam == FAM_OCC) {
         if ((rc = occ_upload(s, slot, Im1, u, chi))) return rc;
     }
+    return FALDOI_OK;
+}
+
+// ---------------------------------------------------------------------------
+// upload with device-side preprocessing (gray, joint normalisation, Gaussian, Lab)
+// ---------------------------------------------------------------------------
+static GaussTaps presmoothing_taps() {
+    // coefficients exactly as gaussian() builds them on the host (src/utils.cpp:541-553), sigma = 0.9
+    GaussTaps t{};
+    const float sigma = 0.90f, den = 2 * sigma * sigma;
+    t.taps = (int)(5 * sigma) + 1;
+    for (int i = 0; i < t.taps; i++) t.k[i] = (float)(1 / (sigma * sqrt(2.0 * 3.1415926)) * expf((float)(-i * i) / den));
+    float norm = 0;
+    for (int i = 0; i < t.taps; i++) norm += t.k[i];
+    norm *= 2;
+    norm -= t.k[0];
+    for (int i = 0; i < t.taps; i++) t.k[i] /= norm;
+    return t;
+}
+
+extern "C" int faldoi_solver_upload_raw(faldoi_solver *s, int slot, const float *i0, const float *i1, const float *im1, int pd,
+                                        const float *u, const float *chi) {
+    if (!s || slot < 0 || slot >= s->B || !i0 || !i1 || !im1 || !u || pd < 1) {
+        set_error("faldoi_solver_upload_raw: bad argument");
+        return FALDOI_ERR_ARG;
+    }
+    const Family fam = method_family(s->method);
+    if (fam == FAM_NLTV && pd < 3) {
+        set_error("the NLTV models need a colour (3-channel) first frame");
+        return FALDOI_ERR_ARG;
+    }
+    if (fam == FAM_OCC && !chi) {
+        set_error("faldoi_solver_upload_raw: method 8 needs chi");
+        return FALDOI_ERR_ARG;
+    }
+    const Geo g = s->g;
+    if (g.h < 5 || g.w < 5) {
+        set_error("gaussian: sigma too large for the image");
+        return FALDOI_ERR_ARG;
+    }
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)g.w * g.h, P = g.plane, B = s->B, need = 3 * (size_t)pd * n;
+    if (need > s->raw_cap) {
+        s->raw_stage = s->dmalloc(need);
+        if (!s->raw_stage) return FALDOI_ERR_MEM;
+        s->raw_cap = need;
+    }
+    if (!s->pp_tmp) {
+        s->pp_tmp = s->dmalloc(P);
+        s->pp_im1 = s->dmalloc(P);
+        s->pp_mm = (unsigned *)s->dmalloc(8);
+        if (!s->pp_tmp || !s->pp_im1 || !s->pp_mm) return FALDOI_ERR_MEM;
+    }
+    const float *src[3] = {i0, i1, im1};
+    for (int k = 0; k < 3; k++)
+        FALDOI_CUDA(cudaMemcpyAsync(s->raw_stage + k * pd * n, src[k], pd * n * sizeof(float), cudaMemcpyDefault, s->stream));
+    static const unsigned mm_init[6] = {0xffffffffu, 0u, 0xffffffffu, 0u, 0xffffffffu, 0u};
+    FALDOI_CUDA(cudaMemcpyAsync(s->pp_mm, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice, s->stream));
+    float *d_i0 = s->I0 + slot * P, *d_i1 = s->I1 + slot * P;
+    float *d_im1 = (fam == FAM_OCC) ? s->occ + (OC_IM1 * B + slot) * P : s->pp_im1;
+    float *dst[3] = {d_i0, d_i1, d_im1};
+    const dim3 blk(32, 8);
+    Geo g1 = g;
+    g1.B = 1;
+    const dim3 grd = grid2d(g1, blk, 1);
+    for (int k = 0; k < 3; k++) gray_minmax_kernel<<<grd, blk, 0, s->stream>>>(s->raw_stage + k * pd * n, pd, dst[k], s->pp_mm + 2 * k, g1);
+    normalize3_kernel<<<grd, blk, 0, s->stream>>>(d_i0, d_i1, d_im1, s->pp_mm, g1);
+    static const GaussTaps taps = presmoothing_taps();
+    for (int k = 0; k < (fam == FAM_OCC ? 3 : 2); k++) {
+        gaussian_pass_kernel<<<grd, blk, 0, s->stream>>>(dst[k], s->pp_tmp, taps, 0, g1);
+        gaussian_pass_kernel<<<grd, blk, 0, s->stream>>>(s->pp_tmp, dst[k], taps, 1, g1);
+    }
+    int rc;
+    if (fam == FAM_TV || fam == FAM_NLTV) {
+        float *set0 = s->state;
+        if ((rc = up2d(s, set0 + (ST_U1 * B + slot) * P, u))) return rc;
+        if ((rc = up2d(s, set0 + (ST_U2 * B + slot) * P, u + n))) return rc;
+        for (int k = ST_XI11; k <= ST_XI22; k++)
+            FALDOI_CUDA(cudaMemsetAsync(set0 + (k * B + slot) * P, 0, P * sizeof(float), s->stream));
+        FALDOI_CUDA(cudaMemsetAsync(s->parity + slot, 0, sizeof(int), s->stream));
+    }
+    if (fam == FAM_NLTV) {
+        image_to_lab_kernel<<<grd, blk, 0, s->stream>>>(s->raw_stage, s->lab + slot * P, s->lab + (B + slot) * P,
+                                                        s->lab + (2 * B + slot) * P, g1);
+        for (int k = 0; k < 2 * NL_SLOTS; k++)
+            FALDOI_CUDA(cudaMemsetAsync(s->dual + (k * B + slot) * P, 0, P * sizeof(float), s->stream));
+    }
+    if (fam == FAM_OCC) {
+        if ((rc = up2d(s, s->occ + (OC_U1 * B + slot) * P, u))) return rc;
+        if ((rc = up2d(s, s->occ + (OC_U2 * B + slot) * P, u + n))) return rc;
+        if ((rc = up2d(s, s->occ + (OC_CHI0 * B + slot) * P, chi))) return rc;
+        FALDOI_CUDA(cudaMemsetAsync(s->occ + (OC_ETA0 * B + slot) * P, 0, P * sizeof(float), s->stream));
+        FALDOI_CUDA(cudaMemsetAsync(s->occ + ((OC_ETA0 + 1) * B + slot) * P, 0, P * sizeof(float), s->stream));
+    }
+    FALDOI_CUDA(cudaGetLastError());
+    return FALDOI_OK;
+}
+
+// test / inspection hook: the preprocessed frames of a slot back to the host (dense w*h each; any may be NULL)
+extern "C" int faldoi_solver_download_frames(faldoi_solver *s, int slot, float *I0n, float *I1n, float *Im1n, float *lab) {
+    if (!s || slot < 0 || slot >= s->B) return FALDOI_ERR_ARG;
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    const Geo g = s->g;
+    const size_t P = g.plane, B = s->B, n = (size_t)g.w * g.h;
+    auto dn = [&](float *dst, const float *src) {
+        return cudaMemcpy2DAsync(dst, g.w * sizeof(float), src, g.pitch * sizeof(float), g.w * sizeof(float), g.h,
+                                 cudaMemcpyDeviceToHost, s->stream);
+    };
+    if (I0n) FALDOI_CUDA(dn(I0n, s->I0 + slot * P));
+    if (I1n) FALDOI_CUDA(dn(I1n, s->I1 + slot * P));
+    if (Im1n && s->occ) FALDOI_CUDA(dn(Im1n, s->occ + (OC_IM1 * B + slot) * P));
+    if (lab && s->lab)
+        for (int c = 0; c < 3; c++) FALDOI_CUDA(dn(lab + c * n, s->lab + (c * B + slot) * P));
+    FALDOI_CUDA(cudaStreamSynchronize(s->stream));
     return FALDOI_OK;
 }
 
@@ -977,6 +1093,21 @@ extern "C" int faldoi_global_solve(int device, const faldoi_params *p, int w, in
     int rc = cached_solver(device, w, h, p->method, &s);
     if (rc != FALDOI_OK) return rc;
     if ((rc = faldoi_solver_upload(s, 0, I0, I1, Im1, lab, u, chi)) != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_run(s, p, 1)) != FALDOI_OK) return rc;
+    return faldoi_solver_download(s, 0, u, chi, log);
+}
+
+extern "C" int faldoi_global_solve_raw(int device, const faldoi_params *p, int w, int h, int pd, const float *i0, const float *i1,
+                                       const float *im1, float *u, float *chi, faldoi_log *log) {
+    if (!p || !i0 || !i1 || !im1 || !u) {
+        set_error("faldoi_global_solve_raw: null argument");
+        return FALDOI_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    faldoi_solver *s = nullptr;
+    int rc = cached_solver(device, w, h, p->method, &s);
+    if (rc != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_upload_raw(s, 0, i0, i1, im1, pd, u, chi)) != FALDOI_OK) return rc;
     if ((rc = faldoi_solver_run(s, p, 1)) != FALDOI_OK) return rc;
     return faldoi_solver_download(s, 0, u, chi, log);
 }

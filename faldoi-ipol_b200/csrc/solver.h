@@ -50,6 +50,11 @@ struct faldoi_solver {
     // NLTV: Lab, weights, duals
     float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *dual = nullptr;
     size_t dual_set_stride = 0;
+    // device-side preprocessing (upload_raw): staging for the raw frames, scratch planes, min/max keys
+    float *raw_stage = nullptr;
+    size_t raw_cap = 0;
+    float *pp_tmp = nullptr, *pp_im1 = nullptr;
+    unsigned *pp_mm = nullptr;
     // OCC planes
     float *occ = nullptr;  // see occ_kernels.cuh for the layout
     // control

@@ -6,7 +6,8 @@
 // Same argv contract, file formats, method ids, parameter defaults and messages; the
 // minimisation itself (tvl2OF / nltvl1_PD / tvcsad_PD / nltvcsad_PD /
 // guided_tvl2coupled_occ) runs on a B200 through the C ABI in include/faldoi_gpu.h.
-// Extra option (ignored by the reference's scripts): -device d  (CUDA device, default 0).
+// Extra options (unknown to the reference's scripts): -device d (CUDA device, default 0),
+// -host_preproc 1 (run main()'s preprocessing on the host instead of the GPU).
 // There is no CPU fallback: without a usable GPU the program reports the error and fails.
 #include <chrono>
 #include <cstdio>
@@ -81,6 +82,7 @@ int main(int argc, char *argv[]) {
     const std::string global_iters = pick_option(args, "glb_iters", "400");
     const std::string verbose_str = pick_option(args, "verbose", "0");
     const std::string device_str = pick_option(args, "device", "0");
+    const bool host_preproc = pick_option(args, "host_preproc", "0") == "1";
 
     if (args.size() != 6 && args.size() != 4) {
         usage(args.size());
@@ -172,19 +174,17 @@ int main(int argc, char *argv[]) {
 
         const bool nltv = (val_method == FALDOI_M_NLTVL1 || val_method == FALDOI_M_NLTVL1_W ||
                            val_method == FALDOI_M_NLTVCSAD || val_method == FALDOI_M_NLTVCSAD_W);
-        std::vector<float> lab;
         if (nltv) {
             std::printf("W:%d H:%d Pd:%d\n", w, h, pd);
             if (pd < 3) {
                 fprintf(stderr, "ERROR: the NLTV models need a colour (3-channel) first frame\n");
                 return EXIT_FAILURE;
             }
-            lab.resize(3 * size);
-            faldoi_host::image_to_lab(i0.data.data(), (int)size, lab.data());
         }
-
-        std::vector<float> i0n(size), i1n(size), i_1n(size);
-        faldoi_host::preprocess(i0.data.data(), i1.data.data(), i_1.data.data(), pd, w, h, i0n.data(), i1n.data(), i_1n.data());
+        if (w < 5 || h < 5) {  // gaussian() aborts with "sigma too large" on such frames
+            fprintf(stderr, "GaussianSmooth: sigma too large\n");
+            return EXIT_FAILURE;
+        }
 
         std::vector<float> u(flow.data);  // u1 | u2
         std::vector<float> chi;
@@ -192,10 +192,25 @@ int main(int argc, char *argv[]) {
 
         if (nltv && (val_method == FALDOI_M_NLTVL1 || val_method == FALDOI_M_NLTVL1_W)) std::printf("Before\nInitialization\n");
 
+        // Everything between reading the files and saving the flow runs on the GPU: gray conversion,
+        // joint normalisation, Gaussian pre-smoothing, Lab (NLTV) and the minimisation itself.
+        // -host_preproc 1 keeps main()'s preprocessing on the host (same bits for gray/normalise/smooth).
         const auto t0 = std::chrono::system_clock::now();
         faldoi_log log{};
-        const int rc = faldoi_global_solve(device, &params, w, h, i0n.data(), i1n.data(), i_1n.data(), nltv ? lab.data() : nullptr,
-                                           u.data(), val_method >= 8 ? chi.data() : nullptr, &log);
+        int rc;
+        if (host_preproc) {
+            std::vector<float> lab, i0n(size), i1n(size), i_1n(size);
+            if (nltv) {
+                lab.resize(3 * size);
+                faldoi_host::image_to_lab(i0.data.data(), (int)size, lab.data());
+            }
+            faldoi_host::preprocess(i0.data.data(), i1.data.data(), i_1.data.data(), pd, w, h, i0n.data(), i1n.data(), i_1n.data());
+            rc = faldoi_global_solve(device, &params, w, h, i0n.data(), i1n.data(), i_1n.data(), nltv ? lab.data() : nullptr, u.data(),
+                                     val_method >= 8 ? chi.data() : nullptr, &log);
+        } else {
+            rc = faldoi_global_solve_raw(device, &params, w, h, pd, i0.data.data(), i1.data.data(), i_1.data.data(), u.data(),
+                                         val_method >= 8 ? chi.data() : nullptr, &log);
+        }
         if (rc != FALDOI_OK) {
             fprintf(stderr, "ERROR: GPU solver failed (%d): %s\n", rc, faldoi_last_error());
             return EXIT_FAILURE;

@@ -88,6 +88,17 @@ void faldoi_solver_destroy(faldoi_solver *s);
 int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0, const float *I1, const float *Im1,
                          const float *lab, const float *u, const float *chi);
 
+/* Same, but from the RAW frames as iio_read_image_float_split returns them (planar, pd
+ * channels, dense w*h per plane, 0..255): main()'s preprocessing -- rgb2gray, the joint
+ * normalisation, gaussian(0.9) and, for the NLTV methods, image_to_lab
+ * (src/global_faldoi.cpp:2042-2068) -- runs on the device.  im1 is the previous frame, or the
+ * I1 pointer again when there is none (what main() does with a 2-line ims.txt).  Gray /
+ * normalise / smooth give the same bits as the host code; Lab is tolerance-level. */
+int faldoi_solver_upload_raw(faldoi_solver *s, int slot, const float *i0, const float *i1, const float *im1, int pd,
+                             const float *u, const float *chi);
+/* Inspection hook: the preprocessed frames of a slot (dense w*h planes; lab 3*w*h; any may be NULL). */
+int faldoi_solver_download_frames(faldoi_solver *s, int slot, float *I0n, float *I1n, float *Im1n, float *lab);
+
 /* Run the primal-dual minimisation on slots [0, npairs) with everything resident in HBM.
  * Replaces the bodies of tvl2OF / nltvl1_PD / tvcsad_PD / nltvcsad_PD /
  * guided_tvl2coupled_occ (dispatch: src/global_faldoi.cpp:2132-2167).
@@ -116,6 +127,11 @@ float *faldoi_solver_device_flow(faldoi_solver *s, int slot, int *pitch_floats);
  * (replaces src/global_faldoi.cpp:2132-2167).  u (and chi) are updated in place. */
 int faldoi_global_solve(int device, const faldoi_params *p, int w, int h, const float *I0, const float *I1,
                         const float *Im1, const float *lab, float *u, float *chi, faldoi_log *log);
+
+/* The same from raw frames (device-side preprocessing, see faldoi_solver_upload_raw): everything
+ * main() does between reading the files and saving the flow. */
+int faldoi_global_solve_raw(int device, const faldoi_params *p, int w, int h, int pd, const float *i0, const float *i1,
+                            const float *im1, float *u, float *chi, faldoi_log *log);
 
 /* ---- per-solver mirrors of the reference's in-process signatures -----------
  * Same argument order and in-place semantics as the reference functions; the

@@ -139,3 +139,41 @@ def test_shared_reciprocal_division_is_ieee(fb):
     bit for bit on its guarded range: 2^31 quotients, random and structured significands."""
     for seed in (1, 2):
         assert fb.selftest_division(1 << 28, seed) == 0
+
+
+@pytest.mark.parametrize("case", ["crop_a", "crop_b"])
+def test_device_preprocessing(fb, po, case):
+    """upload_raw: gray / joint normalisation / Gaussian on the device are bit-identical to the reference's
+    (golden I0n, I1n, Im1n); Lab goes through the device's pow/exp and is tolerance-level."""
+    g = load_case(case)
+    raw = [np.ascontiguousarray(g[k].astype(np.float32)) for k in ("rgb_i0", "rgb_i1", "rgb_im1")]
+    _, h, w = raw[0].shape
+    s = fb.Solver(w, h, 8, 1)
+    s.upload_raw(0, raw[0], raw[1], raw[2], g["u0"], g["chi0"])
+    I0n, I1n, Im1n, _ = s.download_frames(0)
+    assert np.array_equal(I0n, g["I0n"]) and np.array_equal(I1n, g["I1n"]) and np.array_equal(Im1n, g["Im1n"])
+    s.close()
+    s = fb.Solver(w, h, 2, 1)
+    s.upload_raw(0, raw[0], raw[1], raw[2], g["u0"])
+    _, _, _, lab = s.download_frames(0)
+    assert np.abs(lab - g["lab"]).max() <= 1e-4 * max(1.0, np.abs(g["lab"]).max())
+    s.close()
+    # gray single-channel input takes the pd == 1 path
+    gray = [po.o_preprocess(*raw)[k] for k in range(3)]  # any (1,h,w) float planes will do as "raw gray" input
+    s = fb.Solver(w, h, 0, 1)
+    s.upload_raw(0, gray[0][None] * 255, gray[1][None] * 255, gray[2][None] * 255, g["u0"])
+    a, b_, _, _ = s.download_frames(0)
+    oa, ob, _ = po.o_preprocess(gray[0][None] * 255, gray[1][None] * 255, gray[2][None] * 255)
+    assert np.array_equal(a, oa) and np.array_equal(b_, ob)
+    s.close()
+
+
+def test_global_solve_raw_matches_reference(fb):
+    g = load_case("crop_b")
+    raw = [np.ascontiguousarray(g[k].astype(np.float32)) for k in ("rgb_i0", "rgb_i1", "rgb_im1")]
+    u, _, its, _ = fb.global_solve_raw(0, raw[0], raw[1], raw[2], g["u0"], warps=3)
+    assert np.array_equal(u, g["u_m0_w3"])
+    u, chi, _, _ = fb.global_solve_raw(8, raw[0], raw[1], raw[2], g["u0"], chi=g["chi0"], warps=1, glb_iters=12)
+    assert np.array_equal(u, g["u_m8_w1_i12"]) and np.array_equal(chi, g["chi_m8_w1_i12"])
+    u, _, _, _ = fb.global_solve_raw(6, raw[0], raw[1], raw[2], g["u0"], warps=1)
+    assert_flow(u, g["u_m6_w1"], exact=False)
