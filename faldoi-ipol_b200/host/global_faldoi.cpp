@@ -15,6 +15,7 @@
 #include <ctime>
 #include <fstream>
 #include <iostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -73,36 +74,18 @@ const char *method_name(int m) {
 
 }  // namespace
 
-int main(int argc, char *argv[]) {
-    print_today();
-    std::vector<std::string> args(argv, argv + argc);
-    const std::string warps_val = pick_option(args, "w", "5");
-    const std::string method_val = pick_option(args, "m", "0");
-    const std::string file_params = pick_option(args, "p", "");
-    const std::string global_iters = pick_option(args, "glb_iters", "400");
-    const std::string verbose_str = pick_option(args, "verbose", "0");
-    const std::string device_str = pick_option(args, "device", "0");
-    const bool host_preproc = pick_option(args, "host_preproc", "0") == "1";
-
-    if (args.size() != 6 && args.size() != 4) {
-        usage(args.size());
-        return EXIT_FAILURE;
-    }
-
+struct Options {
     int val_method, nwarps, glb_it, device;
-    bool verbose;
-    try {
-        val_method = std::stoi(method_val);
-        nwarps = std::stoi(warps_val);
-        glb_it = std::stoi(global_iters);
-        device = std::stoi(device_str);
-        if (verbose_str != "0" && verbose_str != "1") throw std::invalid_argument("-verbose takes 0 or 1");
-        verbose = (verbose_str == "1");
-    } catch (const std::exception &e) {
-        fprintf(stderr, "ERROR: bad option value (%s)\n", e.what());
-        return EXIT_FAILURE;
-    }
+    bool verbose, host_preproc;
+    std::string file_params;
+};
 
+// one invocation of the reference executable: positional = {argv0, ims.txt, in.flo, out.flo[, occ_in, occ_out]}
+static int run_pair(const std::vector<std::string> &args, const Options &opt) {
+    int val_method = opt.val_method;
+    const int nwarps = opt.nwarps, glb_it = opt.glb_it, device = opt.device;
+    const bool verbose = opt.verbose, host_preproc = opt.host_preproc;
+    const std::string &file_params = opt.file_params;
     const std::string &filename_images = args[1];
     const std::string &image_flow_name = args[2];
     const std::string &outfile = args[3];
@@ -240,6 +223,72 @@ int main(int argc, char *argv[]) {
         fprintf(stderr, "ERROR: %s\n", e.what());
         return EXIT_FAILURE;
     }
+    return EXIT_SUCCESS;
+}
+
+int main(int argc, char *argv[]) {
+    print_today();
+    std::vector<std::string> args(argv, argv + argc);
+    const std::string warps_val = pick_option(args, "w", "5");
+    const std::string method_val = pick_option(args, "m", "0");
+    const std::string file_params = pick_option(args, "p", "");
+    const std::string global_iters = pick_option(args, "glb_iters", "400");
+    const std::string verbose_str = pick_option(args, "verbose", "0");
+    const std::string device_str = pick_option(args, "device", "0");
+    const bool host_preproc = pick_option(args, "host_preproc", "0") == "1";
+    // Sequence mode (not in the reference): -seq jobs.txt, one job per line with the positional
+    // arguments of a normal call ("ims.txt in.flo out.flo [occ_in.png occ_out.png]").  All jobs run
+    // in this process with the options given on the command line, so CUDA start-up and the HBM
+    // allocations are paid once per sequence instead of once per pair.
+    const std::string seq_file = pick_option(args, "seq", "");
+
+    if (seq_file.empty() && args.size() != 6 && args.size() != 4) {
+        usage(args.size());
+        return EXIT_FAILURE;
+    }
+
+    Options opt;
+    try {
+        opt.val_method = std::stoi(method_val);
+        opt.nwarps = std::stoi(warps_val);
+        opt.glb_it = std::stoi(global_iters);
+        opt.device = std::stoi(device_str);
+        if (verbose_str != "0" && verbose_str != "1") throw std::invalid_argument("-verbose takes 0 or 1");
+        opt.verbose = (verbose_str == "1");
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ERROR: bad option value (%s)\n", e.what());
+        return EXIT_FAILURE;
+    }
+    opt.host_preproc = host_preproc;
+    opt.file_params = file_params;
+
+    int rc = EXIT_SUCCESS;
+    if (seq_file.empty()) {
+        rc = run_pair(args, opt);
+    } else {
+        std::ifstream jobs(seq_file);
+        if (!jobs) {
+            fprintf(stderr, "ERROR: cannot open job list '%s'\n", seq_file.c_str());
+            return EXIT_FAILURE;
+        }
+        std::string line;
+        int njobs = 0;
+        while (std::getline(jobs, line)) {
+            std::vector<std::string> job{args[0]};
+            std::string tok;
+            for (std::istringstream ls(line); ls >> tok;) job.push_back(tok);
+            if (job.size() == 1) continue;
+            if (job.size() != 4 && job.size() != 6) {
+                fprintf(stderr, "ERROR: job %d of '%s' needs 3 or 5 file names\n", njobs + 1, seq_file.c_str());
+                return EXIT_FAILURE;
+            }
+            const int r = run_pair(job, opt);
+            if (r != EXIT_SUCCESS) return r;
+            njobs++;
+        }
+        fprintf(stderr, "sequence: %d pairs done\n", njobs);
+    }
+    if (rc != EXIT_SUCCESS) return rc;
     print_today();
     return EXIT_SUCCESS;
 }

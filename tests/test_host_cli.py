@@ -163,3 +163,39 @@ def test_cli_two_frames_falls_back_from_occ(H, tmp_path, po):
                        capture_output=True, text=True)
     assert r.returncode == 0 and "method is changed to TV-l2 coupled" in r.stderr
     assert os.path.exists(out)
+
+
+@pytest.mark.gpu
+def test_cli_fullsize_real_pair_is_bit_identical_to_reference(H, tmp_path, po):
+    """The drop-in claim end to end: same PNG frames, same local_faldoi flow, our executable (own PNG
+    decoder, device preprocessing, GPU solver) writes the same .flo as the reference executable did."""
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "clean_easy")
+    if not os.path.exists(os.path.join(D, "var_m0.flo")):
+        pytest.skip("oracle/_ref/data/clean_easy not present")
+    names = [os.path.join(D, "frame_%04d.png" % k) for k in (2, 3, 1, 4)]
+    (tmp_path / "ims.txt").write_text("\n".join(names) + "\n")
+    out = str(tmp_path / "out.flo")
+    import time
+    t = time.time()
+    r = subprocess.run([BIN, str(tmp_path / "ims.txt"), os.path.join(D, "rg.flo"), out, "-m", "0", "-w", "5", "-verbose", "1"],
+                       capture_output=True, text=True)
+    wall = time.time() - t
+    assert r.returncode == 0, r.stderr
+    iters = [int(x) for x in re.findall(r"Warping: \d+,Iter: (\d+)", r.stderr)]
+    assert iters == [400, 152, 100, 82, 136]
+    assert open(out, "rb").read() == open(os.path.join(D, "var_m0.flo"), "rb").read()
+    print("CLI wall %.2f s; %s" % (wall, [l for l in r.stdout.splitlines() if "All tasks" in l]))
+
+
+@pytest.mark.gpu
+def test_cli_sequence_mode(H, tmp_path, po):
+    """-seq jobs.txt: several pairs in one process (one CUDA start-up), each result as in a single call."""
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po)
+    outs = [str(tmp_path / ("o%d.flo" % k)) for k in range(3)]
+    (tmp_path / "jobs.txt").write_text("".join("%s %s %s\n" % (ims, flo, o) for o in outs))
+    r = subprocess.run([BIN, "-seq", str(tmp_path / "jobs.txt"), "-m", "0", "-w", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "sequence: 3 pairs done" in r.stderr
+    for o in outs:
+        assert np.array_equal(po.read_flo(o), g["u_m0_w3"])
