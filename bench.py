@@ -6,7 +6,7 @@
 
 A "step" = one global_faldoi pass (all warps, all iterations) over one batch of synthetic
 1024x436 pairs per GPU (BASELINE.json configs[4]: the 64-pair sequence sharded by pair; default
-16 pairs per GPU, `--pairs-per-gpu 64` for the whole sequence on one GPU).  Pairs are independent
+64 pairs resident per GPU, i.e. the whole named sequence on every GPU).  Pairs are independent
 -> no data-path collective, weak scaling.  Work is counted as pixels x iterations actually run
 (the TVL2 loop exits early per pair, src/global_faldoi.cpp:684), so launches that find a pair
 already converged cost time but add no work.
@@ -15,9 +15,10 @@ already converged cost time but add no work.
            on the solver's stream, max over ranks.
   e2e    : the same through the C-ABI with pinned HOST buffers: H2D of I0,I1,u per pair, solve, D2H of
            the flow, wall clock between device syncs, max over ranks.
-  roofline: the per-iteration kernel (tv_iter_kernel): algorithmic 80 B/px/iter x
-           pixel-iterations run / time inside the iteration launches (events around every warp's
-           iteration loop, faldoi_solver_last_iter_ms) vs the measured HBM copy bandwidth.
+  roofline: the iteration kernel (tv_tile2_kernel, two iterations per launch): algorithmic 80 B/px/iter
+            x pixel-iterations run / time inside the iteration launches (events around
+           every warp's iteration loop, faldoi_solver_last_iter_ms) vs the measured HBM copy bandwidth.
+           `traffic` = DRAM bytes of ONE launch (ncu, 16-pair capture scaled to this batch).
   cpu_baseline: the UNMODIFIED reference tvl2OF (oracle/_ref, OpenMP, all host cores) on ONE pair of
            the same workload (about 5-10 s); falls back to the C port (oracle/) if the reference
            build did not travel.
@@ -43,7 +44,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=16)
+    ap.add_argument("--pairs-per-gpu", type=int, default=64,
+                    help="pairs resident per GPU; 64 = the whole named 64-pair sequence on every GPU (weak scaling)")
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--height", type=int, default=436)
     ap.add_argument("--method", type=int, default=0)
@@ -314,6 +316,8 @@ def main():
         ach = alg * units_step * a.steps / (iter_ms / 1e3) / 1e9
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         traffic = json.load(open(prof)).get(str(method)) if os.path.exists(prof) else None
+        if traffic is not None:
+            traffic = traffic * B / 16.0  # the ncu capture had 16 pairs per launch; bytes scale with the pairs
         nplanes_in = 4 + (1 if method == 8 else 0) * 2 + (3 if need_lab else 0)
         line = dict(base, value=value, ms_per_step=1e3 * t_res / a.steps,
                     e2e={"value": e2e, "unit": "Mpix*iter/s", "h2d_bytes_per_step": B * nplanes_in * npix * 4,
@@ -321,7 +325,8 @@ def main():
                          "pairs_per_s": world * B * a.steps / t_e2e},
                     pairs_per_s=world * B * a.steps / t_res, iters_per_pair=iters_total / B,
                     gpu_launches=int(launches_all),
-                    roofline={"bound": "hbm", "kernel": "tv_iter_kernel" if method in (0, 1, 4, 5) else "iter kernels",
+                    roofline={"bound": "hbm", "kernel": {0: "tv_tile2_kernel", 1: "tv_tile2_kernel", 4: "tv_tile_kernel<CSAD>", 5: "tv_tile_kernel<CSAD>", 2: "nltv_iter_kernel", 3: "nltv_iter_kernel",
+                                         6: "nltv_iter_kernel<CSAD>", 7: "nltv_iter_kernel<CSAD>", 8: "occ_xi_rows_kernel + occ_chi_rows_kernel"}[method],
                               "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                               "alg_bytes_per_px_iter": alg, "traffic": traffic},
                     clocks=clocks)
