@@ -177,3 +177,16 @@ def test_global_solve_raw_matches_reference(fb):
     assert np.array_equal(u, g["u_m8_w1_i12"]) and np.array_equal(chi, g["chi_m8_w1_i12"])
     u, _, _, _ = fb.global_solve_raw(6, raw[0], raw[1], raw[2], g["u0"], warps=1)
     assert_flow(u, g["u_m6_w1"], exact=False)
+
+
+@pytest.mark.parametrize("max_iters,tol", [(1, 0.0), (2, 0.0), (3, 0.0), (7, 0.0), (400, 10.0), (400, 0.02)])
+def test_exit_iteration_corner_cases(fb, po, max_iters, tol):
+    """Two iterations run per launch: odd iteration caps, an exit after the very first iteration and
+    exits that fall on the first / second half of a launch must all reproduce the reference loop."""
+    I0, I1, _, u0, _ = synthetic_pair(150, 40, seed=11)
+    p = fb.default_params(0, warps=3)
+    p.max_iters, p.tol = max_iters, tol
+    u, _, its, errs = fb.global_solve(0, I0, I1, u0, params=p)
+    ou, _, oits, oerrs = po.o_tvl2(I0, I1, u0, tol=tol, warps=3, max_iter=max_iters)
+    assert its == oits and errs == oerrs
+    assert np.array_equal(u, ou)
