@@ -98,9 +98,32 @@ __device__ __forceinline__ void t2_dual_quad(Tile2Smem &S, int r, int qi, int gx
         x22[k] = x22[k] + tau * u2y;
     }
     if (big > 1.f) {
+        // Some pixel of the quad is saturated: divide all four by max(1,|xi|) with the shared-reciprocal
+        // fast path (x/1 is exact there too) under ONE range test for the quad; anything unusual
+        // (zero / tiny / huge numerator, huge norm) takes IEEE division for the whole quad.
+        bool ok = big < 1e6f;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (nr[k] > 1.f) div4_shared(x11[k], x12[k], x21[k], x22[k], nr[k]);
+            ok = ok && fastdiv_nz_ok(x11[k]) && fastdiv_nz_ok(x12[k]) && fastdiv_nz_ok(x21[k]) && fastdiv_nz_ok(x22[k]);
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float d = fmaxf(1.f, nr[k]), rr = rcp_refined(d);
+                x11[k] = div_by_rcp(x11[k], d, rr);
+                x12[k] = div_by_rcp(x12[k], d, rr);
+                x21[k] = div_by_rcp(x21[k], d, rr);
+                x22[k] = div_by_rcp(x22[k], d, rr);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float d = fmaxf(1.f, nr[k]);
+                x11[k] /= d;
+                x12[k] /= d;
+                x21[k] /= d;
+                x22[k] /= d;
+            }
+        }
     }
     *reinterpret_cast<float4 *>(S.xi(0, r) + cx) = make_float4(x11[0], x11[1], x11[2], x11[3]);
     *reinterpret_cast<float4 *>(S.xi(1, r) + cx) = make_float4(x12[0], x12[1], x12[2], x12[3]);
@@ -110,8 +133,12 @@ __device__ __forceinline__ void t2_dual_quad(Tile2Smem &S, int r, int qi, int gx
 
 // divergence, TH, primal step and extrapolation of one column quad of relative row r.
 // Returns max |du|^2 over the quad's pixels that are inside the frame.  Results go to o1,o2,ob1,ob2.
-__device__ __forceinline__ float t2_primal_quad(Tile2Smem &S, const TvArgs &a, int r, int qi, int gx0, int gy, int w, int hg,
-                                                float (&o1)[4], float (&o2)[4], float (&ob1)[4], float (&ob2)[4]) {
+// FAST = true evaluates the three divisions per pixel (TH quotient, two (u-v)/theta) with the
+// branch-free fast paths and reports in `unsafe` whether any operand left their validated range;
+// the caller then repeats the quad with FAST = false (IEEE division), so the bits never differ.
+template <bool FAST>
+__device__ __forceinline__ float t2_primal_quad_impl(Tile2Smem &S, const TvArgs &a, int r, int qi, int gx0, int gy, int w, int hg,
+                                                     float (&o1)[4], float (&o2)[4], float (&ob1)[4], float (&ob2)[4], bool &unsafe) {
     const int cx = 4 * qi;
     const float tau = a.tau, l_t = a.l_t;
     const float4 M11 = *reinterpret_cast<const float4 *>(S.xi(0, r) + cx);
@@ -148,20 +175,52 @@ __device__ __forceinline__ float t2_primal_quad(Tile2Smem &S, const TvArgs &a, i
         const float grad = ix[k] * ix[k] + iy[k] * iy[k];
         const float rho = cc[k] + (ix[k] * u1[k] + iy[k] * u2[k]);
         const float thr = l_t * grad;
-        float sc = -rho / grad;
-        sc = grad_is_zero(grad) ? 0.f : sc;
-        sc = (rho > thr) ? -l_t : sc;
-        sc = (rho < -l_t * grad) ? l_t : sc;
+        const bool gz = grad_is_zero(grad), hi = (rho > thr), lo = (rho < -l_t * grad);
+        float sc;
+        if (FAST) {
+            const bool used = !(gz | hi | lo);       // the quotient is only consumed inside the band
+            const float gs = used ? grad : 1.f;      // keeps the unused lanes free of inf / nan
+            sc = div_by_rcp(-rho, gs, rcp_refined(gs));
+            sc = (rho == 0.f) ? -rho : sc;           // signed zero exactly as IEEE: (-(+-0)) / grad
+            unsafe |= used && !(fastdiv_num_ok(rho) && grad < 1e6f);
+        } else {
+            sc = -rho / grad;
+        }
+        sc = gz ? 0.f : sc;
+        sc = hi ? -l_t : sc;
+        sc = lo ? l_t : sc;
         const float v1 = u1[k] + sc * ix[k];
         const float v2 = u2[k] + sc * iy[k];
-        o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
-        o2[k] = u2[k] - tau * (-d2 + div_const(u2[k] - v2, a.dth));
+        const float x1 = u1[k] - v1, x2 = u2[k] - v2;
+        float q1, q2;
+        if (FAST) {  // Markstein sequence with RN(1/theta), exhaustively verified for this theta (DivConst)
+            q1 = __fmaf_rn(__fmaf_rn(-(x1 * a.dth.rb), a.dth.b, x1), a.dth.rb, x1 * a.dth.rb);
+            q2 = __fmaf_rn(__fmaf_rn(-(x2 * a.dth.rb), a.dth.b, x2), a.dth.rb, x2 * a.dth.rb);
+            q1 = (x1 == 0.f) ? x1 : q1;  // +-0 / theta keeps its sign
+            q2 = (x2 == 0.f) ? x2 : q2;
+            const float a1 = fabsf(x1), a2 = fabsf(x2);
+            unsafe |= (a1 != 0.f && !(a1 > 1e-30f && a1 < 1e30f)) || (a2 != 0.f && !(a2 > 1e-30f && a2 < 1e30f));
+        } else {
+            q1 = x1 / a.dth.b;
+            q2 = x2 / a.dth.b;
+        }
+        o1[k] = u1[k] - tau * (-d1 + q1);
+        o2[k] = u2[k] - tau * (-d2 + q2);
         const float e = (o1[k] - u1[k]) * (o1[k] - u1[k]) + (o2[k] - u2[k]) * (o2[k] - u2[k]);
         if (gx >= 0 && gx < w) emax = fmaxf(emax, e);
         ob1[k] = 2 * o1[k] - u1[k];
         ob2[k] = 2 * o2[k] - u2[k];
     }
     return emax;
+}
+
+__device__ __forceinline__ float t2_primal_quad(Tile2Smem &S, const TvArgs &a, int r, int qi, int gx0, int gy, int w, int hg,
+                                                float (&o1)[4], float (&o2)[4], float (&ob1)[4], float (&ob2)[4]) {
+    bool unsafe = !a.dth.ok;  // theta's reciprocal sequence failed its verification: IEEE division throughout
+    float e = 0.f;
+    if (!unsafe) e = t2_primal_quad_impl<true>(S, a, r, qi, gx0, gy, w, hg, o1, o2, ob1, ob2, unsafe);
+    if (unsafe) e = t2_primal_quad_impl<false>(S, a, r, qi, gx0, gy, w, hg, o1, o2, ob1, ob2, unsafe);
+    return e;
 }
 
 struct T2Args {
