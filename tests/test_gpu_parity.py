@@ -190,3 +190,40 @@ def test_exit_iteration_corner_cases(fb, po, max_iters, tol):
     ou, _, oits, oerrs = po.o_tvl2(I0, I1, u0, tol=tol, warps=3, max_iter=max_iters)
     assert its == oits and errs == oerrs
     assert np.array_equal(u, ou)
+
+
+@pytest.mark.parametrize("lam,theta,tau", [(23.4547299737, 0.283263949386, 0.125), (40.0, 0.25, 0.2), (15.0, 0.683018503834, 0.0739776273913)])
+def test_custom_parameters_tvl2(fb, po, lam, theta, tau):
+    """-p files change lambda/theta/tau for methods 0,1,8 (README 'best params'): the constant-divisor
+    fast path is re-verified per theta on the device and must stay bit-exact."""
+    I0, I1, _, u0, _ = synthetic_pair(200, 56, seed=21)
+    p = fb.default_params(0, warps=2)
+    p.lambda_, p.theta, p.tau = lam, theta, tau
+    u, _, its, errs = fb.global_solve(0, I0, I1, u0, params=p)
+    ou, _, oits, oerrs = po.o_tvl2(I0, I1, u0, lam=lam, theta=theta, tau=tau, warps=2)
+    assert its == oits and errs == oerrs
+    assert np.array_equal(u, ou)
+
+
+def test_custom_parameters_occ(fb, po, tmp_path):
+    """Method 8 reads all nine scalars of the -p file."""
+    g = load_case("crop_b")
+    f = tmp_path / "p.txt"
+    f.write_text("23.4547299737\n0.283263949386\n0.125\n0.701945704713\n0.0706776435878\n0.0739776273913\n0.0839911992024\n0.134077646787\n1.4058686732\n")
+    p = fb.default_params(8, glb_iters=6, warps=1, params_file=str(f))
+    u, chi, its, _ = fb.global_solve(8, g["I0n"], g["I1n"], g["u0"], Im1=g["Im1n"], chi=g["chi0"], params=p)
+    op = po.default_params()
+    op.lambda_, op.theta, op.beta = p.lambda_, p.theta, p.beta
+    ou, ochi, oits, _ = po.o_global_solve(8, g["I0n"], g["I1n"], g["Im1n"], None, g["u0"], g["chi0"], params=op, warps=1, glb_iters=6)
+    assert its == oits
+    assert np.array_equal(u, ou) and np.array_equal(chi, ochi)
+
+
+def test_zero_warps_and_single_pixel_rows(fb, po):
+    I0, I1, _, u0, _ = synthetic_pair(64, 5, seed=3)
+    p = fb.default_params(0, warps=0)
+    u, _, its, _ = fb.global_solve(0, I0, I1, u0, params=p)
+    assert its == [] and np.array_equal(u, u0)
+    u, _, its, _ = fb.global_solve(0, I0, I1, u0, warps=1)
+    ou, _, oits, _ = po.o_global_solve(0, I0, I1, None, None, u0, warps=1)
+    assert its == oits and np.array_equal(u, ou)
