@@ -230,10 +230,16 @@ def main():
     d = make_pairs(B, w, h, 1000 + rank * B, dev)
     need_lab = method in (2, 3, 6, 7)
     lab = None
-    if need_lab:  # Lab conversion is host preprocessing in the reference's main(); done once, outside the timed region
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import pyoracle as po
-        lab = torch.from_numpy(np.stack([po.o_image_to_lab(np.ascontiguousarray(x)) for x in d["rgb"].cpu().numpy()])).to(dev)
+    if need_lab:
+        # Lab conversion is preprocessing (once, outside the timed region): the product's own host
+        # library does it (libfaldoi_host.so, include/faldoi_host.h) -- not the oracle.
+        import ctypes as C
+        hostlib = C.CDLL(os.path.join(ROOT, "faldoi-ipol_b200", "libfaldoi_host.so"))
+        rgb = np.ascontiguousarray(d["rgb"].cpu().numpy())
+        lab_np = np.empty_like(rgb)
+        for k in range(B):
+            hostlib.faldoi_host_image_to_lab(rgb[k].ctypes.data_as(C.c_void_p), w, h, lab_np[k].ctypes.data_as(C.c_void_p))
+        lab = torch.from_numpy(lab_np).to(dev)
     chi = torch.zeros(B, h, w, device=dev) if method == 8 else None
     host = {k: d[k].cpu().pin_memory() for k in ("I0", "I1", "Im1", "u0")}
     host_lab = lab.cpu().pin_memory() if lab is not None else None
