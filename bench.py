@@ -352,7 +352,7 @@ def main():
 
 
 def main_stripes(a, rank, base):
-    """BASELINE.json configs[4], second half: 3840x2160 pair, row stripes + per-iteration halo exchange."""
+    """BASELINE.json configs[4], second half: 3840x2160 pair, row stripes + 2-row halo exchange once per two-iteration launch."""
     import numpy as np
     import torch
     if rank != 0:
@@ -392,14 +392,14 @@ def main_stripes(a, rank, base):
     units = npix * iters
     peak, peak_src = peak_hbm()
     ach = 80 * units * a.steps / (dev_ms / 1e3) / 1e9
-    cfg = dict(base["config"], workload="synthetic %dx%d pair cut into %d row stripes (one per GPU), halo rows exchanged every "
-               "iteration by NVLink peer stores from the iteration kernel; TVL2, %d warps x <=400 iters" % (w, h, ng, a.warps),
+    cfg = dict(base["config"], workload="synthetic %dx%d pair cut into %d row stripes (one per GPU), two halo rows per side exchanged once "
+               "per two-iteration launch by NVLink peer stores from the iteration kernel; TVL2, %d warps x <=400 iters" % (w, h, ng, a.warps),
                width=w, height=h, pairs_per_gpu=None, l2_policy="state %.1f GB >> L2" % (23 * npix * 4 / 1e9))
     line = dict(base, config=cfg, scaling="strong", value=units * a.steps / (dev_ms / 1e3) / 1e6,
                 ms_per_step=dev_ms / a.steps, iters_per_pair=iters, gpu_launches=int(launches),
                 e2e={"value": units * a.steps / t_e2e / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": (ng + 3) * npix * 4,
                      "d2h_bytes_per_step": 2 * npix * 4},
-                roofline={"bound": "hbm", "kernel": "tv_tile_kernel", "achieved": ach, "peak": peak * ng, "peak_source": peak_src +
+                roofline={"bound": "hbm", "kernel": "tv_tile2_kernel", "achieved": ach, "peak": peak * ng, "peak_source": peak_src +
                           " x %d GPUs" % ng, "unit": "GB/s", "frac": ach / (peak * ng), "alg_bytes_per_px_iter": 80, "traffic": None},
                 clocks=clocks)
     print(json.dumps(line))

@@ -346,6 +346,32 @@ __global__ void __launch_bounds__(T2_THREADS, 3) tv_tile2_kernel(const __grid_co
             st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
             st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
             st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+            // Row stripes (one frame over several GPUs): the two owned rows next to a stripe boundary are the
+            // neighbour's two halo rows -- store them straight into its planes through the NVLink peer mapping.
+            if (a.peer_up && y < a.g.own_lo + 2) {
+                float *po = a.peer_up + (size_t)(par_in ^ 1) * a.peer_up_set + (size_t)(a.peer_up_row + y - a.g.own_lo) * pitch + gx0;
+                const size_t pp = a.peer_up_plane;
+                st4(po + ST_XI11 * pp, *reinterpret_cast<const float4 *>(S.xi(0, r) + cx));
+                st4(po + ST_XI12 * pp, *reinterpret_cast<const float4 *>(S.xi(1, r) + cx));
+                st4(po + ST_XI21 * pp, *reinterpret_cast<const float4 *>(S.xi(2, r) + cx));
+                st4(po + ST_XI22 * pp, *reinterpret_cast<const float4 *>(S.xi(3, r) + cx));
+                st4(po + ST_U1 * pp, make_float4(o1[0], o1[1], o1[2], o1[3]));
+                st4(po + ST_U2 * pp, make_float4(o2[0], o2[1], o2[2], o2[3]));
+                st4(po + ST_UB1 * pp, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+                st4(po + ST_UB2 * pp, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+            }
+            if (a.peer_dn && y >= a.g.own_hi - 2) {
+                float *po = a.peer_dn + (size_t)(par_in ^ 1) * a.peer_dn_set + (size_t)(a.peer_dn_row + y - (a.g.own_hi - 2)) * pitch + gx0;
+                const size_t pp = a.peer_dn_plane;
+                st4(po + ST_XI11 * pp, *reinterpret_cast<const float4 *>(S.xi(0, r) + cx));
+                st4(po + ST_XI12 * pp, *reinterpret_cast<const float4 *>(S.xi(1, r) + cx));
+                st4(po + ST_XI21 * pp, *reinterpret_cast<const float4 *>(S.xi(2, r) + cx));
+                st4(po + ST_XI22 * pp, *reinterpret_cast<const float4 *>(S.xi(3, r) + cx));
+                st4(po + ST_U1 * pp, make_float4(o1[0], o1[1], o1[2], o1[3]));
+                st4(po + ST_U2 * pp, make_float4(o2[0], o2[1], o2[2], o2[3]));
+                st4(po + ST_UB1 * pp, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
+                st4(po + ST_UB2 * pp, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+            }
         }
     }
 

@@ -77,6 +77,30 @@ def make_fullsize_anchor():
                         epe_out=epe(var), u_sub=var[:, ::8, ::8].copy(), gt_sub=gt[:, ::8, ::8].copy())
 
 
+def make_fullsize_others():
+    """Methods 4, 7, 8 on the whole clean/easy pair (reference CLI runs of oracle/run_full_refs.sh,
+    7-13 minutes each on 8 cores): per-warp iteration counts, EPE vs ground truth, sub-sampled flow."""
+    import re
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "clean_easy")
+    gt = po.read_flo(os.path.join(REF, "example_data", "clean", "easy", "gt", "frame_0002.flo"))
+    epe = lambda a: float(np.sqrt(((a - gt) ** 2).sum(0)).mean())
+    for m in (4, 7, 8):
+        f = os.path.join(D, "var_m%d.flo" % m)
+        if not os.path.exists(f):
+            print("skip method", m, "(run oracle/run_full_refs.sh first)")
+            continue
+        var = po.read_flo(f)
+        log = open(os.path.join(D, "log_m%d.txt" % m)).read()
+        iters = [int(x) for x in re.findall(r"Warping: \d+, ?Iter: (\d+)", log)]
+        out = dict(iters=np.array(iters), epe_out=epe(var), u_sub=var[:, ::8, ::8].copy())
+        if m == 8:
+            from PIL import Image
+            out["chi_sub"] = np.asarray(Image.open(os.path.join(D, "var_m8_occ.png")))[::4, ::4].copy()
+            out["chi_count"] = int(np.asarray(Image.open(os.path.join(D, "var_m8_occ.png"))).sum())
+        print("full-size m%d iters %s EPE %.4f" % (m, iters, out["epe_out"]))
+        np.savez_compressed(os.path.join(OUT, "fullsize_clean_easy_m%d.npz" % m), **out)
+
+
 if __name__ == "__main__":
     assert po.have_ref(), "build the reference first: make -C oracle ref"
     # 96x64 crop, every energy model (the reference always runs 400 iterations for methods 0-7)
@@ -84,3 +108,4 @@ if __name__ == "__main__":
     # ragged size (w, h not multiples of 4 or of the tile), touching the image border region
     make_case("crop_b", "clean/easy", 3, 5, 61, 45, [(0, 3, 400), (4, 1, 400), (2, 1, 400), (6, 1, 400), (8, 1, 12)])
     make_fullsize_anchor()
+    make_fullsize_others()

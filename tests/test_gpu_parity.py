@@ -227,3 +227,43 @@ def test_zero_warps_and_single_pixel_rows(fb, po):
     u, _, its, _ = fb.global_solve(0, I0, I1, u0, warps=1)
     ou, _, oits, _ = po.o_global_solve(0, I0, I1, None, None, u0, warps=1)
     assert its == oits and np.array_equal(u, ou)
+
+
+@pytest.mark.parametrize("method", [4, 7, 8])
+def test_fullsize_reference_pair_other_models(fb, po, method):
+    """BASELINE configs 2-4 at full size: the reference CLI's result on clean/easy (oracle/run_full_refs.sh,
+    minutes of CPU each) vs one GPU solve.  TV-CSAD and TVL2-OCC bit for bit, NLTV-CSAD(-W) within the north
+    star's tolerance; EPE against the Sintel ground truth equal to 3 decimals."""
+    import os
+    from conftest import ROOT, GOLDEN
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "clean_easy")
+    gfile = os.path.join(GOLDEN, "fullsize_clean_easy_m%d.npz" % method)
+    init = os.path.join(D, "rg_m8.flo" if method == 8 else "rg.flo")
+    if not os.path.exists(gfile) or not os.path.exists(init):
+        pytest.skip("full-size golden / inputs not present")
+    g = dict(np.load(gfile))
+    fr = [po.read_image_planar(os.path.join(D, "frame_%04d.png" % k)) for k in (1, 2, 3)]
+    u0 = po.read_flo(init)
+    chi0 = None
+    if method == 8:
+        from PIL import Image
+        chi0 = np.asarray(Image.open(os.path.join(D, "rg_occ.png"))).astype(np.float32)
+    u, chi, its, _ = fb.global_solve_raw(method, fr[1], fr[2], fr[0], u0, chi=chi0, warps=5, glb_iters=400)
+    assert its == list(g["iters"])
+    gt = po.read_flo(os.path.join(D, "gt_frame_0002.flo"))
+    epe = float(np.sqrt(((u - gt) ** 2).sum(0)).mean())
+    assert round(epe, 3) == round(float(g["epe_out"]), 3)
+    if method == 7:
+        d = np.abs(u[:, ::8, ::8] - g["u_sub"])
+        assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, (d.mean(), d.max())
+        full = os.path.join(D, "var_m7.flo")
+        if os.path.exists(full):
+            d = np.abs(u - po.read_flo(full))
+            assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, (d.mean(), d.max())
+    else:
+        assert np.array_equal(u[:, ::8, ::8], g["u_sub"])
+        full = os.path.join(D, "var_m%d.flo" % method)
+        if os.path.exists(full):
+            assert np.array_equal(u, po.read_flo(full))
+    if method == 8:
+        assert np.array_equal(chi[::4, ::4].astype(np.uint8), g["chi_sub"]) and int(chi.sum()) == int(g["chi_count"])
