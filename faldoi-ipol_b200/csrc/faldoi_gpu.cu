@@ -206,6 +206,7 @@ static int make_tile_maps(faldoi_solver *s) {
     if ((rc = make_plane_map(&s->maps.c0, c0, g, g.B, TT_W, TT_H))) return rc;
     if ((rc = make_plane_map(&s->maps.ix, s->Ix, g, g.B, TT_W, TT_H))) return rc;
     if ((rc = make_plane_map(&s->maps.iy, s->Iy, g, g.B, TT_W, TT_H))) return rc;
+    if (method_is_csad(s->method) && (rc = make_plane_map(&s->maps.sep, s->csad_sep, g, (size_t)CSAD_SEPS * g.B, TT_W, TT_H))) return rc;
     if (!method_is_csad(s->method)) {  // boxes of the two-iteration kernel (2-pixel apron)
         if ((rc = make_plane_map(&s->maps2.ub, s->state, g, nstate, T2_PW, T2_UB_ROWS))) return rc;
         if ((rc = make_plane_map(&s->maps2.xi, s->state, g, nstate, T2_PW, T2_XI_ROWS))) return rc;
@@ -294,9 +295,8 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
         if (method_is_csad(method)) {
             ALLOC(s->scale, B * P);
             ALLOC(s->I1w, B * P);
-            ALLOC(s->bs, 48 * B * P);
-            s->csad_hint = (unsigned char *)s->dmalloc((B * P + 3) / 4);
-            if (!s->csad_hint) return fail(FALDOI_ERR_MEM);
+            ALLOC(s->csad_blk, CSAD_FLOATS * B * P);
+            ALLOC(s->csad_sep, CSAD_SEPS * B * P);
         } else {
             ALLOC(s->rho_c, B * P);
         }
@@ -316,7 +316,7 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
     // function attributes are per device: opt the tile kernels into 97 KB of dynamic shared memory here
     if (!cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
                  "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
+        !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename TileSmemFor<DATA_CSAD>::type) + 128),
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(tv_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
                  "cudaFuncSetAttribute"))
@@ -596,7 +596,7 @@ template <int DATA>
 static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
     if (use_tile_kernel()) {
         const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
-        tv_tile_kernel<DATA><<<grid, TT_THREADS, sizeof(TileSmem) + 128, s->stream>>>(s->maps, a, it);
+        tv_tile_kernel<DATA><<<grid, TT_THREADS, sizeof(typename TileSmemFor<DATA>::type) + 128, s->stream>>>(s->maps, a, it);
         return;
     }
     const dim3 block(32, 8);
@@ -635,8 +635,8 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.Iy = s->Iy;
     a.rho_c = s->rho_c;
     a.scale = s->scale;
-    a.bs = s->bs;
-    a.csad_hint = s->csad_hint;
+    a.blk = s->csad_blk;
+    a.sep = s->csad_sep;
     a.err_max = s->err_max;
     a.err_chk = s->err_max;
     a.err_sum = s->err_sum;
@@ -698,13 +698,12 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             ca.parity = s->parity;
             ca.set_stride = s->set_stride;
             ca.scale = s->scale;
-            ca.bs = s->bs;
+            ca.blk = s->csad_blk;
+            ca.sep = s->csad_sep;
             ca.g = g;
             ca.hyp = 1;
             const dim3 cb(32, 4);
             csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
-            // the residuals were re-sorted: restart the rank hints from the middle (24 of 48)
-            FALDOI_CUDA(cudaMemsetAsync(s->csad_hint, 24, (size_t)g.B * g.plane, s->stream));
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
@@ -799,8 +798,8 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.Iy = s->Iy;
     a.rho_c = s->rho_c;
     a.scale = s->scale;
-    a.bs = s->bs;
-    a.csad_hint = s->csad_hint;
+    a.blk = s->csad_blk;
+    a.sep = s->csad_sep;
     a.err_sum = s->err_sum;
     a.g = g;
     a.max_iters = p->max_iters;
@@ -842,13 +841,12 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             ca.parity = s->parity;
             ca.set_stride = s->set_stride;
             ca.scale = s->scale;
-            ca.bs = s->bs;
+            ca.blk = s->csad_blk;
+            ca.sep = s->csad_sep;
             ca.g = g;
             ca.hyp = 0;
             const dim3 cb(32, 4);
             csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
-            // the residuals were re-sorted: restart the rank hints from the middle (24 of 48)
-            FALDOI_CUDA(cudaMemsetAsync(s->csad_hint, 24, (size_t)g.B * g.plane, s->stream));
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
@@ -1255,3 +1253,4 @@ extern "C" int faldoi_selftest_division(int device, unsigned long long n, unsign
     FALDOI_CUDA(e);
     return FALDOI_OK;
 }
+

@@ -81,8 +81,7 @@ struct NlArgs {
     float *dual;        // [2][2*NL_SLOTS][B]: P slots then Q slots
     size_t dual_set_stride;
     const float *wgt, *wt;   // [24][B], [B]
-    const float *Ix, *Iy, *rho_c, *scale, *bs;
-    unsigned char *csad_hint;
+    const float *Ix, *Iy, *rho_c, *scale, *blk, *sep;  // blk/sep: CSAD table, see csad_select
     double *err_sum;    // [B][max_iters]
     Geo g;
     int max_iters;
@@ -148,8 +147,7 @@ __global__ void __launch_bounds__(256, 4) nltv_iter_kernel(NlArgs a, int it, int
             if (sc != 0.f) {  // 0 marks grad <= GRAD_IS_ZERO (:1734)
                 const float s = (ix * u1 + iy * u2) / sc;
                 const int np = csad_count(x, y, w, h);
-                const CsadProbe pr = csad_probe(a.bs + (off + p) * 48, np, a.csad_hint[off + p]);
-                const float med = csad_select(a.bs + (off + p) * 48, np, s, l_t, sc, pr, a.csad_hint + off + p);
+                const float med = csad_select(a.blk, a.sep, a.g, b, y, x, np, s, l_t, sc);
                 v1 = u1 - ix * med / sc;
                 v2 = u2 - iy * med / sc;
             }

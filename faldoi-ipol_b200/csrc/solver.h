@@ -41,8 +41,8 @@ struct faldoi_solver {
     // TV / NLTV state (2 ping-pong sets) and per-warp constants
     float *state = nullptr;
     size_t set_stride = 0;
-    float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr, *bs = nullptr;
-    unsigned char *csad_hint = nullptr;  // [B][plane] bytes
+    float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr;
+    float *csad_blk = nullptr, *csad_sep = nullptr;  // CSAD two-level sorted residual table (csad_select): CSAD_FLOATS per pixel, CSAD_SEPS separator planes
     faldoi::TileMaps maps{};             // TMA descriptors of the tile kernel (TV family)
     faldoi::Tile2Maps maps2{};           // ... of the two-iteration TVL2 kernel
     unsigned char *t2_stat = nullptr;    // [B][t2_stride] launch status of the two-iteration kernel

@@ -33,9 +33,9 @@ struct TvArgs {
     const float *Ix, *Iy;  // [B] warped gradient of I1
     const float *rho_c;    // [B] TVL1 data term constant
     const float *scale;    // [B] CSAD: hypot(Ix^2+Iy^2, 0.01)
-    const float *bs;       // [B][plane][48] CSAD: per pixel, its neighbour residuals b_j sorted descending (one 192-byte
-                           // record per pixel, so the two probes of a warm-started search share a 32-byte sector)
-    unsigned char *csad_hint;  // [B] bytes per pixel: last iteration's rank m* (see csad_select)
+    const float *blk;      // CSAD level 2: per pixel, its neighbour residuals b_j sorted descending, in blocks of
+                           // CSAD_BR ranks (see csad_select)
+    const float *sep;      // [CSAD_SEPS][B] planes, CSAD level 1: the sorted residual that ends each block
     unsigned *err_max;     // [B][max_iters] float bits of max |du|^2     (DATA_TVL1), written by this handle
     const unsigned *err_chk;  // what the exit test reads: err_max, or the max over all stripes of a stripe group
     double *err_sum;       // [B][max_iters] sum of |du|^2                  (DATA_CSAD)
@@ -68,63 +68,86 @@ __device__ __forceinline__ bool pair_active(const TvArgs &a, int b, int it) {
 // rank selection of the CSAD data term (src/global_faldoi.cpp:1549-1570): the
 // element of index n+1 of sort({-(b_j - s)} U {(n-2k)*l_t*scale, k=0..n}).
 // With a_m = -(bs_m - s) ascending (bs sorted descending) and the thresholds
-// t_m descending, that element equals min_m max(a_m, t_m), m = 0..n-1, found
-// by bisection on the monotone predicate a_m >= t_m  ("CSAD rank").
-struct CsadProbe {
-    int c;         // rank tried first: last iteration's m*
-    float bc, bl;  // sorted residuals at ranks c and c-1 (raw, before the shift by s)
+// t_m descending, that element equals min_m max(a_m, t_m) = min(a_{m*}, t_{m*-1}) where
+// m* = number of ranks whose predicate a_m >= t_m is false (the predicate is monotone in m;
+// DESIGN.md, "CSAD rank").  s moves a lot from one iteration to the next (measured: m* jumps by more
+// than 8 ranks for a quarter of the pixels), so instead of a data-dependent chain of probes the
+// sorted residuals are kept as a two-level table:
+//   level 1  separator planes (the last rank of every block but the final one), dense, streamed
+//            with the other planes;
+//   level 2  blocks of CSAD_BR consecutive ranks, one aligned slot per block.
+// One gather per pixel, no dependent loads, 15 comparisons.  Slots of ranks >= np hold -inf: their
+// predicate is true and their a is +inf, which is what the reference's shorter list amounts to.
+// Default: 4 blocks of 12 ranks in 64-byte slots, the 4 slots of a pixel adjacent (256 B / pixel).
+// FALDOI_CSAD_BR=8 selects 6 blocks of 8 ranks laid out [row][block][x][8], where neighbours that
+// pick the same block share a 128-byte line: 21 % less HBM traffic (HBM delivers whole lines either
+// way) but measured 20 % slower on B200 (profiles/README.md), so it is not the default.
+#ifndef FALDOI_CSAD_BR
+#define FALDOI_CSAD_BR 12
+#endif
+enum {
+    CSAD_BR = FALDOI_CSAD_BR,            // ranks per block
+    CSAD_BLOCKS = 48 / CSAD_BR,
+    CSAD_SEPS = CSAD_BLOCKS - 1,
+    CSAD_QV = CSAD_BR / 4,               // float4 per block
+    CSAD_FLOATS = CSAD_BR == 12 ? 64 : 48  // table floats per pixel
+};
+static_assert(CSAD_BR == 12 || CSAD_BR == 8, "FALDOI_CSAD_BR must be 12 or 8");
+
+struct CsadBlock {
+    float4 q[CSAD_QV];
 };
 
-// Issue the two probe loads of the warm-started search early (they do not depend on the
-// current flow), so their HBM latency overlaps other work of the kernel.
-__device__ __forceinline__ CsadProbe csad_probe(const float *__restrict__ bs, int np, unsigned char hint) {
-    CsadProbe pr;
-    pr.c = min((int)hint, np);
-    pr.bc = (pr.c < np) ? __ldg(bs + pr.c) : 0.f;
-    pr.bl = (pr.c > 0) ? __ldg(bs + pr.c - 1) : 0.f;
-    return pr;
+__device__ __forceinline__ float csad_t(int np, int m, float l_t, float scale) { return (float)(np - 2 * m) * l_t * scale; }
+
+// level 1: the block that holds m* = number of separators whose predicate is false
+__device__ __forceinline__ int csad_sep_false(float sep_k, int k, int np, float s, float l_t, float scale) {
+    return (-(sep_k - s) >= csad_t(np, CSAD_BR * k + CSAD_BR - 1, l_t, scale)) ? 0 : 1;
 }
 
-__device__ __forceinline__ float csad_select(const float *__restrict__ bs, int np, float s, float l_t, float scale,
-                                             const CsadProbe &pr, unsigned char *hint_out) {
-    // m* = first m in [0, np) with a_m >= t_m (np if none); the answer is min(a_{m*}, t_{m*-1}).
-    // m* moves slowly from one iteration to the next (s changes little), so last iteration's m*
-    // is tried first with two independent probes; only if it moved is the bisection run on the
-    // side the probes point to.  Any route finds the same m*, hence the same value.
-    auto a_at = [&](int m) { return -(__ldg(bs + m) - s); };  // bs: this pixel's 48 sorted residuals (192 contiguous bytes)
-    auto t_at = [&](int m) { return (float)(np - 2 * m) * l_t * scale; };
-    int lo = 0, hi = np;
-    float a_hi = 0.f;  // a(hi) whenever hi < np
-    const int c = pr.c;
-    {
-        const float ac = -(pr.bc - s), al = -(pr.bl - s);
-        const bool pc = (c == np) || (ac >= t_at(c));    // predicate holds at c
-        const bool pl = (c > 0) && (al >= t_at(c - 1));  // predicate holds at c-1
-        if (pc && !pl) {
-            lo = hi = c;
-            a_hi = ac;
-        } else if (pl) {  // m* <= c-1
-            hi = c - 1;
-            a_hi = al;
-        } else {  // predicate false at c: m* > c
-            lo = c + 1;
-        }
+// level 2: the residuals of block j (ranks CSAD_BR*j ..) -> the selected value
+__device__ __forceinline__ float csad_finish(const CsadBlock &B, int j, int np, float s, float l_t, float scale) {
+    float v[CSAD_BR];
+#pragma unroll
+    for (int i = 0; i < CSAD_QV; i++) v[4 * i] = B.q[i].x, v[4 * i + 1] = B.q[i].y, v[4 * i + 2] = B.q[i].z, v[4 * i + 3] = B.q[i].w;
+    const float fb = (float)(np - 2 * CSAD_BR * j);  // np - 2*(BR*j+i) = fb - 2i, exact in fp32
+    int cnt = 0;
+    float amin = INFINITY;  // a_{m*}: the smallest a whose predicate holds (+inf if m* is past the last residual)
+#pragma unroll
+    for (int i = 0; i < CSAD_BR; i++) {
+        const float am = -(v[i] - s);
+        const float tm = (fb - (float)(2 * i)) * l_t * scale;
+        const bool pr = am >= tm;
+        cnt += pr ? 0 : 1;
+        amin = pr ? fminf(amin, am) : amin;
     }
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const float am = a_at(mid);
-        if (am >= t_at(mid)) {
-            hi = mid;
-            a_hi = am;
-        } else {
-            lo = mid + 1;
-        }
-    }
-    *hint_out = (unsigned char)lo;
-    float ans = INFINITY;
-    if (lo < np) ans = a_hi;
-    if (lo > 0) ans = fminf(ans, t_at(lo - 1));
-    return ans;
+    const int m = CSAD_BR * j + cnt;
+    const float tprev = (m > 0) ? csad_t(np, m - 1, l_t, scale) : INFINITY;
+    return fminf(amin, tprev);
+}
+
+// float index of rank 0 of block j of pixel (x, y) of pair b.  plane >= h * pitch.
+__device__ __forceinline__ size_t csad_slot_index(const Geo &g, int b, int y, int x, int j) {
+    if (CSAD_BR == 12) return ((size_t)b * g.plane + (size_t)y * g.pitch + x) * 64 + j * 16;
+    return (size_t)b * g.plane * 48 + ((size_t)y * CSAD_BLOCKS + j) * g.pitch * 8 + (size_t)x * 8;
+}
+
+__device__ __forceinline__ CsadBlock csad_gather(const float *__restrict__ blk, const Geo &g, int b, int y, int x, int j) {
+    const float4 *q = reinterpret_cast<const float4 *>(blk + csad_slot_index(g, b, y, x, j));
+    CsadBlock B;
+#pragma unroll
+    for (int i = 0; i < CSAD_QV; i++) B.q[i] = __ldg(q + i);
+    return B;
+}
+
+// whole lookup with plain loads (march kernel, NLTV-CSAD)
+__device__ __forceinline__ float csad_select(const float *__restrict__ blk, const float *__restrict__ sep, const Geo &g, int b, int y, int x,
+                                             int np, float s, float l_t, float scale) {
+    const size_t pix = (size_t)b * g.plane + (size_t)y * g.pitch + x, ss = (size_t)g.B * g.plane;
+    int j = 0;
+#pragma unroll
+    for (int k = 0; k < CSAD_SEPS; k++) j += csad_sep_false(__ldg(sep + k * ss + pix), k, np, s, l_t, scale);
+    return csad_finish(csad_gather(blk, g, b, y, x, j), j, np, s, l_t, scale);
 }
 
 // Norm used by TV-CSAD's row-wise projection, max(1, hypotf(a,b)) (tvcsad_getD :1433-1443).
@@ -338,9 +361,7 @@ __global__ void __launch_bounds__(256, 2) tv_iter_kernel(TvArgs a, int it) {
                 if (gx < w) {
                     const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / sc[k];
                     const int np = csad_count(gx, y, w, h);
-                    const size_t pp = (size_t)b * plane + (size_t)y * pitch + gx;
-                    const CsadProbe pr = csad_probe(a.bs + pp * 48, np, a.csad_hint[pp]);
-                    const float med = csad_select(a.bs + pp * 48, np, s, l_t, sc[k], pr, a.csad_hint + pp);
+                    const float med = csad_select(a.blk, a.sep, a.g, b, y, gx, np, s, l_t, sc[k]);
                     v1 = u1[k] - ix[k] * med / sc[k];
                     v2 = u2[k] - iy[k] * med / sc[k];
                 }
@@ -406,8 +427,9 @@ __global__ void __launch_bounds__(256, 2) tv_iter_kernel(TvArgs a, int it) {
 // CSAD per-warp constants (src/global_faldoi.cpp:1514-1534): scale =
 // hypot(Ix^2+Iy^2, 0.01) and, for the in-image neighbours j of the 7x7 window,
 //   b_j = (I0[p] - I0[j] - I1w[p] + I1w[j] + Ix*u1 + Iy*u2) / scale
-// stored SORTED DESCENDING per pixel (a 48-float record) so the per-iteration rank
-// selection is a bisection instead of the reference's std::sort of 97 floats.
+// stored SORTED DESCENDING per pixel as the two-level table of csad_select (blocks of CSAD_BR
+// ranks + separator planes) so the per-iteration rank selection is 15 comparisons
+// instead of the reference's std::sort of 97 floats.
 // hyp = 0 is the NLTV-CSAD variant (:1698-1723): scale = sqrt(Ix^2+Iy^2),
 // only where Ix^2+Iy^2 > 1e-8 (elsewhere scale := 0 marks "v = u").
 // ---------------------------------------------------------------------------
@@ -417,7 +439,8 @@ struct CsadArgs {
     const int *parity;
     size_t set_stride;
     float *scale;  // [B]
-    float *bs;     // [B][plane][48]
+    float *blk;    // csad_slot_index layout
+    float *sep;    // [CSAD_SEPS][B][plane]
     Geo g;
     int hyp;
 };
@@ -470,7 +493,8 @@ __global__ void __launch_bounds__(128) csad_constants_kernel(CsadArgs a) {
         int rank = 0;
 #pragma unroll
         for (int j = 0; j < 48; j++) rank += (bv[j] > bv[i]) || (bv[j] == bv[i] && j < i);
-        a.bs[(off + p) * 48 + rank] = bv[i];
+        a.blk[csad_slot_index(a.g, b, y, x, rank / CSAD_BR) + rank % CSAD_BR] = bv[i];
+        if (rank % CSAD_BR == CSAD_BR - 1 && rank < 47) a.sep[(size_t)(rank / CSAD_BR) * a.g.B * a.g.plane + off + p] = bv[i];
     }
 }
 

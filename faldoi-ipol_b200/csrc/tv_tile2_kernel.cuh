@@ -285,10 +285,10 @@ __global__ void __launch_bounds__(T2_THREADS, 3) tv_tile2_kernel(const __grid_co
         while (!done) {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                 "selp.u32 %0, 1, 0, p;\n\t}\n"
                 : "=r"(done)
-                : "r"(smem_u32(&S.bar)), "r"(0)
+                : "r"(smem_u32(&S.bar)), "r"(0), "r"(FALDOI_MBAR_SUSPEND_NS)
                 : "memory");
         }
     }

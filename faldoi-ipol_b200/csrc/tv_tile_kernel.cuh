@@ -65,7 +65,30 @@ struct TileSmem {
 struct TileMaps {
     CUtensorMap ub, xi, pl;  // the state array [2 sets][ST_COUNT][B]: boxes 136x(H+2), 136x(H+1), 128xH
     CUtensorMap c0, ix, iy;  // per-warp constants [B]: box 128xH
+    CUtensorMap sep;         // CSAD level-1 separators [CSAD_SEPS][B]: box 128xH
 };
+
+// TV-CSAD additionally stages the separator planes of the two-level rank table
+struct TileSmemCsad : TileSmem {
+    alignas(128) float sep_[CSAD_SEPS][TT_PL_FLOATS];
+    __device__ __forceinline__ float *sep(int k, int row) { return &sep_[k][row * TT_W]; }
+};
+template <int DATA>
+struct TileSmemFor {
+    typedef TileSmem type;
+};
+// FALDOI_CSAD_SEP_GLOBAL=1 (default): the separators are read with coalesced float4 loads in phase 2;
+// 0 stages them with TMA like the other planes (12 KB more shared memory; measured 4 % slower at 16
+// pairs).  4 CTAs/SM (64 registers) spills and is 25 % slower, see profiles/README.md.
+#ifndef FALDOI_CSAD_SEP_GLOBAL
+#define FALDOI_CSAD_SEP_GLOBAL 1
+#endif
+#if !FALDOI_CSAD_SEP_GLOBAL
+template <>
+struct TileSmemFor<DATA_CSAD> {
+    typedef TileSmemCsad type;
+};
+#endif
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -81,7 +104,8 @@ template <int DATA>
 __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS_CSAD : FALDOI_TT_CTAS) tv_tile_kernel(const __grid_constant__ TileMaps maps, TvArgs a, int it) {
     // (no pointer arithmetic on the base: it would demote every access from LDS/STS to generic LD/ST)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+    typedef typename TileSmemFor<DATA>::type Smem;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int b = blockIdx.z;
     const int par0 = a.parity[b];  // issued together with the error word read by pair_active: one L2 round trip
     if (!pair_active<DATA>(a, b, it)) return;
@@ -96,34 +120,13 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
     const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
     float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
 
-    // CSAD: this thread's phase-2 quad is known now; fetch its four rank hints (one 4-byte load) and
-    // the two probe values per pixel before anything else, so their latency hides behind the
-    // staging wait and phase 1.
-    CsadProbe probe[4];
-    unsigned char *hint_ptr = nullptr;
-    bool csad_task = false;
-    if (DATA == DATA_CSAD) {
-        const int r = tid >> 5, q = tid & 31;
-        const int y = y0 + r, gx0 = x0 + 4 * q;
-        csad_task = (r < rows && gx0 < w && y >= a.g.own_lo && y < a.g.own_hi);
-        if (csad_task) {
-            const size_t pp = (size_t)b * plane + (size_t)y * pitch + gx0;
-            hint_ptr = a.csad_hint + pp;
-            const uchar4 h4 = *reinterpret_cast<const uchar4 *>(hint_ptr);
-            const unsigned char hh[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (gx0 + k < w) probe[k] = csad_probe(a.bs + (pp + k) * 48, csad_count(gx0 + k, y + yo, w, hg), hh[k]);
-        }
-    }
-
     // ---- stage the tile: one thread arms the mbarrier and issues the 11 TMA box loads ----
     const int ub_lo = (y0 > 0) ? -1 : 0;
     const int xi_lo = ub_lo, xi_hi = rows - 1;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"((unsigned)TT_TX_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"((unsigned)(TT_TX_BYTES + (DATA == DATA_CSAD && !FALDOI_CSAD_SEP_GLOBAL ? CSAD_SEPS * TT_PL_FLOATS * 4 : 0))) : "memory");
         const int B = a.g.B, zs = par * ST_COUNT * B + b;
         tma_box(S.ub(0, 0), &maps.ub, x0 - 4, y0 - 1, zs + ST_UB1 * B, &S.bar);
         tma_box(S.ub(1, 0), &maps.ub, x0 - 4, y0 - 1, zs + ST_UB2 * B, &S.bar);
@@ -134,6 +137,12 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         tma_box(S.pl(2, 0), &maps.c0, x0, y0, b, &S.bar);
         tma_box(S.pl(3, 0), &maps.ix, x0, y0, b, &S.bar);
         tma_box(S.pl(4, 0), &maps.iy, x0, y0, b, &S.bar);
+#if !FALDOI_CSAD_SEP_GLOBAL
+        if constexpr (DATA == DATA_CSAD) {
+#pragma unroll
+            for (int k = 0; k < CSAD_SEPS; k++) tma_box(S.sep(k, 0), &maps.sep, x0, y0, k * B + b, &S.bar);
+        }
+#endif
     }
     // wait for the bytes (phase 0): one thread polls the mbarrier, the other warps sleep on the CTA
     // barrier instead of burning issue slots in a spin loop (the acquire of the poller is carried
@@ -143,10 +152,10 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         while (!done) {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                 "selp.u32 %0, 1, 0, p;\n\t}\n"
                 : "=r"(done)
-                : "r"(smem_u32(&S.bar)), "r"(0)
+                : "r"(smem_u32(&S.bar)), "r"(0), "r"(FALDOI_MBAR_SUSPEND_NS)
                 : "memory");
         }
     }
@@ -234,6 +243,46 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         if (gx0 >= pitch || y < a.g.own_lo || y >= a.g.own_hi) continue;  // halo rows belong to the neighbour stripe
         const int gy = y + yo;
         const bool interior = gx0 > 0 && gx0 + 4 < w && gy > 0 && gy < hg - 1;  // no frame border in this quad
+        const float4 U1 = *reinterpret_cast<const float4 *>(S.pl(0, r) + 4 * q);
+        const float4 U2 = *reinterpret_cast<const float4 *>(S.pl(1, r) + 4 * q);
+        const float4 C0 = *reinterpret_cast<const float4 *>(S.pl(2, r) + 4 * q);
+        const float4 IX = *reinterpret_cast<const float4 *>(S.pl(3, r) + 4 * q);
+        const float4 IY = *reinterpret_cast<const float4 *>(S.pl(4, r) + 4 * q);
+        const float u1[4] = {U1.x, U1.y, U1.z, U1.w}, u2[4] = {U2.x, U2.y, U2.z, U2.w};
+        const float cc[4] = {C0.x, C0.y, C0.z, C0.w};
+        const float ix[4] = {IX.x, IX.y, IX.z, IX.w}, iy[4] = {IY.x, IY.y, IY.z, IY.w};
+        // CSAD rank selection (csad_select in tv_kernels.cuh): level 1 from the separator planes picks each
+        // pixel's block of ranks, the four blocks are gathered with independent loads (one HBM
+        // latency for the quad, no dependent chain), level 2 finishes in registers.
+        float med[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (DATA == DATA_CSAD) {
+            float sv[4];
+            int jb[4] = {0, 0, 0, 0}, np[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                sv[k] = (ix[k] * u1[k] + iy[k] * u2[k]) / cc[k];
+                np[k] = csad_count(min(gx0 + k, w - 1), gy, w, hg);
+            }
+#pragma unroll
+            for (int j = 0; j < CSAD_SEPS; j++) {
+#if FALDOI_CSAD_SEP_GLOBAL
+                const float4 E = __ldg(reinterpret_cast<const float4 *>(a.sep + ((size_t)j * a.g.B + b) * plane + (size_t)y * pitch + gx0));
+#else
+                const float4 E = *reinterpret_cast<const float4 *>(S.sep(j, r) + 4 * q);
+#endif
+                const float e[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) jb[k] += csad_sep_false(e[k], j, np[k], sv[k], l_t, cc[k]);
+            }
+            CsadBlock blk[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (gx0 + k >= w) jb[k] = 0;  // (pitch padding: separators are not written there)
+                blk[k] = csad_gather(a.blk, a.g, b, y, min(gx0 + k, w - 1), jb[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) med[k] = csad_finish(blk[k], jb[k], np[k], sv[k], l_t, cc[k]);
+        }
         const float4 M11 = *reinterpret_cast<const float4 *>(S.xi(0, r + 1) + cx);
         const float4 M12 = *reinterpret_cast<const float4 *>(S.xi(1, r + 1) + cx);
         const float4 M21 = *reinterpret_cast<const float4 *>(S.xi(2, r + 1) + cx);
@@ -241,17 +290,9 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         const float4 T12 = *reinterpret_cast<const float4 *>(S.xi(1, r) + cx);
         const float4 T22 = *reinterpret_cast<const float4 *>(S.xi(3, r) + cx);
         const float l11 = S.xi(0, r + 1)[cx - 1], l21 = S.xi(2, r + 1)[cx - 1];
-        const float4 U1 = *reinterpret_cast<const float4 *>(S.pl(0, r) + 4 * q);
-        const float4 U2 = *reinterpret_cast<const float4 *>(S.pl(1, r) + 4 * q);
-        const float4 C0 = *reinterpret_cast<const float4 *>(S.pl(2, r) + 4 * q);
-        const float4 IX = *reinterpret_cast<const float4 *>(S.pl(3, r) + 4 * q);
-        const float4 IY = *reinterpret_cast<const float4 *>(S.pl(4, r) + 4 * q);
         const float m11[4] = {M11.x, M11.y, M11.z, M11.w}, m12[4] = {M12.x, M12.y, M12.z, M12.w};
         const float m21[4] = {M21.x, M21.y, M21.z, M21.w}, m22[4] = {M22.x, M22.y, M22.z, M22.w};
         const float p12[4] = {T12.x, T12.y, T12.z, T12.w}, p22[4] = {T22.x, T22.y, T22.z, T22.w};
-        const float u1[4] = {U1.x, U1.y, U1.z, U1.w}, u2[4] = {U2.x, U2.y, U2.z, U2.w};
-        const float cc[4] = {C0.x, C0.y, C0.z, C0.w};
-        const float ix[4] = {IX.x, IX.y, IX.z, IX.w}, iy[4] = {IY.x, IY.y, IY.z, IY.w};
         float o1[4], o2[4], ob1[4], ob2[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -282,12 +323,8 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
                 v1 = u1[k];
                 v2 = u2[k];
                 if (gx < w) {
-                    const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / cc[k];
-                    const int np = csad_count(gx, gy, w, hg);
-                    const float med = csad_select(a.bs + ((size_t)b * plane + (size_t)y * pitch + gx) * 48, np, s, l_t, cc[k], probe[k],
-                                                  hint_ptr + k);
-                    v1 = u1[k] - ix[k] * med / cc[k];
-                    v2 = u2[k] - iy[k] * med / cc[k];
+                    v1 = u1[k] - ix[k] * med[k] / cc[k];
+                    v2 = u2[k] - iy[k] * med[k] / cc[k];
                 }
             }
             o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
