@@ -306,8 +306,15 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
         ALLOC(s->lab, 3 * B * P);
         ALLOC(s->wgt, (size_t)NL_SLOTS * B * P);
         ALLOC(s->wt, B * P);
+        ALLOC(s->rwt, B * P);
         s->dual_set_stride = (size_t)2 * NL_SLOTS * B * P;
         ALLOC(s->dual, 2 * s->dual_set_stride);
+        if (make_plane_map(&s->nlmaps.dual, s->dual, s->g, (size_t)4 * NL_SLOTS * B, NLT_W, NLT_H) ||
+            make_plane_map(&s->nlmaps.rec, s->dual, s->g, (size_t)4 * NL_SLOTS * B, NLT_PW, NLT_H) ||
+            make_plane_map(&s->nlmaps.wgt, s->wgt, s->g, (size_t)NL_SLOTS * B, NLT_W, NLT_H) ||
+            make_plane_map(&s->nlmaps.ub, s->state, s->g, (size_t)2 * ST_COUNT * B, NLT_PW, NLT_AR) ||
+            make_plane_map(&s->nlmaps.rwt, s->rwt, s->g, B, NLT_PW, NLT_AR))
+            return fail(FALDOI_ERR_CUDA);
     }
     if (fam == FAM_OCC) {
         ALLOC(s->occ, (size_t)OCC_PLANES * B * P);
@@ -319,6 +326,10 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
         !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename TileSmemFor<DATA_CSAD>::type) + 128),
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(tv_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
+                 "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
+                 "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
                  "cudaFuncSetAttribute"))
         return fail(FALDOI_ERR_CUDA);
     if (!cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize")) return fail(FALDOI_ERR_CUDA);
@@ -784,7 +795,7 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         const float difS = (float)hypot((double)l, (double)k);
         offs.ws[sl] = expf(-difS / 2.f);
     }
-    nltv_init_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->lab, s->wgt, s->wt, offs, g);
+    nltv_init_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->lab, s->wgt, s->wt, s->rwt, offs, g);
     centered_gradient_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->I1, s->I1x, s->I1y, g);
     s->launches += 2;
     NlArgs a{};
@@ -850,11 +861,21 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
+        // FALDOI_NLTV_KERNEL=simple selects the first version (one thread per pixel, plain loads)
+        static const bool tiled = !(getenv("FALDOI_NLTV_KERNEL") && !strcmp(getenv("FALDOI_NLTV_KERNEL"), "simple"));
+        const dim3 tgrid((g.pitch + NLT_W - 1) / NLT_W, (g.h + NLT_H - 1) / NLT_H, npairs);
+        const size_t tsm = sizeof(NlTileSmem) + 128;
         for (int it = 0; it < p->max_iters; it++) {
-            if (csad)
+            if (tiled) {
+                if (csad)
+                    nltv_tile_kernel<DATA_CSAD><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
+                else
+                    nltv_tile_kernel<DATA_TVL1><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
+            } else if (csad) {
                 nltv_iter_kernel<DATA_CSAD><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
-            else
+            } else {
                 nltv_iter_kernel<DATA_TVL1><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
+            }
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         s->launches += p->max_iters;

@@ -16,12 +16,19 @@ enum { NL_SLOTS = 24 };
 
 // The NLTV models are held to the north star's fp32 tolerance, not to bit equality (their
 // weights already differ from glibc's expf in the last bit), so the 192 divisions per pixel
-// and iteration of the dual updates use the 2-ulp approximate division (MUFU.RCP + FMUL).
+// and iteration of the dual updates are a * rcp.approx(b) (MUFU.RCP + FMUL, 2 ulp).  Every
+// divisor here is 1 + tau*|g| >= 1 or a weight sum, far from the 2^126 range where the approximate
+// reciprocal needs the rescaling that __fdividef wraps around it (2 more FMUL + a compare each).
 // Build with -DFALDOI_NLTV_IEEE_DIV for IEEE division.
+__device__ __forceinline__ float nl_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 #ifdef FALDOI_NLTV_IEEE_DIV
 #define NL_DIV(a, b) ((a) / (b))
 #else
-#define NL_DIV(a, b) __fdividef((a), (b))
+#define NL_DIV(a, b) ((a) * nl_rcp(b))
 #endif
 
 struct NlOffsets {
@@ -41,7 +48,7 @@ __host__ __device__ __forceinline__ void nl_slot_offset(int s, int &k, int &l) {
 // float (the reference calls glibc expf; see DESIGN.md "NLTV weights").
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nltv_init_kernel(const float *__restrict__ lab, float *__restrict__ wgt,
-                                                        float *__restrict__ wt, NlOffsets offs, Geo g) {
+                                                        float *__restrict__ wt, float *__restrict__ rwt, NlOffsets offs, Geo g) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int b = blockIdx.z;
@@ -73,6 +80,7 @@ __global__ void __launch_bounds__(256) nltv_init_kernel(const float *__restrict_
         wgt[(size_t)s * ks + off + p] = wv;
     }
     wt[off + p] = ne;
+    rwt[off + p] = NL_DIV(1.f, ne);  // what the iteration multiplies by (nltv_tile_kernel reads this plane)
 }
 
 struct NlArgs {
@@ -80,7 +88,7 @@ struct NlArgs {
     size_t set_stride;
     float *dual;        // [2][2*NL_SLOTS][B]: P slots then Q slots
     size_t dual_set_stride;
-    const float *wgt, *wt;   // [24][B], [B]
+    const float *wgt, *wt;   // [24][B], [B]   (+ rwt = 1/wt, read through a tensor map by nltv_tile_kernel)
     const float *Ix, *Iy, *rho_c, *scale, *blk, *sep;  // blk/sep: CSAD table, see csad_select
     double *err_sum;    // [B][max_iters]
     Geo g;

@@ -1,0 +1,272 @@
+// Tiled, TMA-pipelined version of the fused NLTV iteration (same math, slot order and
+// interface as nltv_iter_kernel in nltv_kernels.cuh; see there for the reference citations).
+//
+// The per-pixel kernel issues ~190 scattered plane loads per pixel and iteration and spends its time
+// on the scoreboard (ncu: 10 of 15.7 cycles per issued instruction are long-scoreboard stalls, 3000
+// instructions per pixel, a third of them address arithmetic).  Here one CTA owns a 128 x 8 pixel tile
+// of one pair (warp = row, lane = 4-pixel quad) and walks the 24 neighbour slots through a 3-stage
+// ring of shared-memory buffers filled by TMA box loads:
+//   per slot s, offset (k,l):   wgt[s], P[s], Q[s]         128 x 8 box at (x0,   y0)    -- own
+//                               P[23-s], Q[23-s]           136 x 8 box at (x0-4, y0+k)  -- the neighbour's
+//                                                          reciprocal duals; the row shift is in the box
+//                                                          origin, the column shift l is applied when
+//                                                          reading shared memory (a box must start on a
+//                                                          16-byte boundary of global memory: an odd
+//                                                          x origin raises "illegal instruction")
+//   once per tile:              ubar1, ubar2, 1/wt         (128+8) x (8+4) apron boxes
+// Loads of slot s+1, s+2 are in flight while slot s is computed; out-of-frame parts of a box are
+// zero-filled by the TMA unit; slots whose neighbour is outside the frame carry a negative weight and
+// are clamped to zero weight, which is the reference's neighbour-in-image test.
+// New duals go straight to HBM as float4.  Algorithmic traffic is unchanged (532 B / pixel / iteration);
+// what changes is who waits for it.
+#pragma once
+#include "nltv_kernels.cuh"
+#include "tv_tile_kernel.cuh"  // tma_box, smem_u32
+
+namespace faldoi {
+
+#ifndef FALDOI_NLT_STAGES
+#define FALDOI_NLT_STAGES 3
+#endif
+enum {
+    NLT_W = 128,
+    NLT_H = 8,
+    NLT_PW = NLT_W + 8,   // apron tile: cols x0-4 .. x0+131
+    NLT_AR = NLT_H + 4,   // apron tile: rows y0-2 .. y0+NLT_H+1
+    NLT_THREADS = 32 * NLT_H,
+    NLT_NS = FALDOI_NLT_STAGES,
+    NLT_TILE = NLT_W * NLT_H,
+    NLT_RTILE = NLT_PW * NLT_H,  // reciprocal-dual box: cols x0-4 .. x0+131
+    NLT_APRON = NLT_AR * NLT_PW
+};
+static_assert((NLT_APRON * 4) % 128 == 0 && (NLT_RTILE * 4) % 128 == 0, "every TMA destination must keep 128-byte alignment");
+
+struct NlTileSmem {
+    float own[NLT_NS][3][NLT_TILE];   // wgt[s], P[s], Q[s]
+    float rec[NLT_NS][2][NLT_RTILE];  // P[23-s], Q[23-s], rows shifted by k, cols x0-4 ..
+    float ub[2][NLT_APRON];
+    float rw[NLT_APRON];
+    double red[NLT_H];
+    unsigned long long full[NLT_NS], cbar;
+};
+
+struct NlTileMaps {
+    CUtensorMap dual;  // [2 sets][48][B] planes, box 128 x 8
+    CUtensorMap rec;   // same array, box 136 x 8
+    CUtensorMap wgt;   // [24][B], box 128 x 8
+    CUtensorMap ub;    // state [2 sets][ST_COUNT][B], box 136 x 12
+    CUtensorMap rwt;   // [B], box 136 x 12
+};
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(FALDOI_MBAR_SUSPEND_NS)
+            : "memory");
+    }
+}
+
+// out[i] = row[i + l], l in -2..2 known at compile time after unrolling: two aligned float4 loads and a
+// static pick instead of four scalar loads (which would be 4-way bank conflicts at a lane stride of 4)
+__device__ __forceinline__ void nl_shifted4(const float *row, int l, float (&out)[4]) {
+    const float4 M = *reinterpret_cast<const float4 *>(row);
+    if (l == 0) {
+        out[0] = M.x, out[1] = M.y, out[2] = M.z, out[3] = M.w;
+    } else if (l < 0) {
+        const float4 L = *reinterpret_cast<const float4 *>(row - 4);
+        const float t[8] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = t[4 + i + l];
+    } else {
+        const float4 H = *reinterpret_cast<const float4 *>(row + 4);
+        const float t[8] = {M.x, M.y, M.z, M.w, H.x, H.y, H.z, H.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = t[i + l];
+    }
+}
+
+template <int DATA>
+__global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_constant__ NlTileMaps maps, NlArgs a, int it, int base_parity) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    NlTileSmem &S = *reinterpret_cast<NlTileSmem *>(smem_raw);
+    const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
+    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch, B = a.g.B;
+    const int x0 = blockIdx.x * NLT_W, y0 = blockIdx.y * NLT_H;
+    const int par = (base_parity + it) & 1;
+    const int zd = par * 2 * NL_SLOTS * B + b;  // plane index of dual slot 0 of this pair in the input set
+    const int zs = par * ST_COUNT * B + b;
+
+    auto issue = [&](int s) {  // one thread: arm the stage's barrier and start its five box loads
+        const int sg = s % NLT_NS, rs = NL_SLOTS - 1 - s;
+        int k, l;
+        nl_slot_offset(s, k, l);
+        (void)l;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.full[sg])), "r"((unsigned)((3 * NLT_TILE + 2 * NLT_RTILE) * 4)) : "memory");
+        tma_box(S.own[sg][0], &maps.wgt, x0, y0, s * B + b, &S.full[sg]);
+        tma_box(S.own[sg][1], &maps.dual, x0, y0, zd + s * B, &S.full[sg]);
+        tma_box(S.own[sg][2], &maps.dual, x0, y0, zd + (NL_SLOTS + s) * B, &S.full[sg]);
+        tma_box(S.rec[sg][0], &maps.rec, x0 - 4, y0 + k, zd + rs * B, &S.full[sg]);
+        tma_box(S.rec[sg][1], &maps.rec, x0 - 4, y0 + k, zd + (NL_SLOTS + rs) * B, &S.full[sg]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NLT_NS; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.full[i])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.cbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.cbar)), "r"((unsigned)(3 * NLT_APRON * 4)) : "memory");
+        tma_box(S.ub[0], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB1 * B, &S.cbar);
+        tma_box(S.ub[1], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB2 * B, &S.cbar);
+        tma_box(S.rw, &maps.rwt, x0 - 4, y0 - 2, b, &S.cbar);
+#pragma unroll
+        for (int s = 0; s < NLT_NS; s++) issue(s);
+    }
+    __syncthreads();  // barrier objects are initialised for everyone
+
+    const int y = y0 + r, gx0 = x0 + 4 * lane;
+    const bool act = (y < h) && (gx0 < w);
+    const size_t plane = a.g.plane, ks = (size_t)B * plane, off = (size_t)b * plane;
+    const size_t o = (size_t)y * pitch + gx0;
+    const float *sin = a.state + (size_t)par * a.set_stride + off;
+    float *sout = a.state + (size_t)(par ^ 1) * a.set_stride + off;
+    float *dout = a.dual + (size_t)(par ^ 1) * a.dual_set_stride + off;
+    const float tau = a.tau, l_t = a.l_t;
+
+    // ---- own pixel data and the data term (plain coalesced float4 loads, once per tile) ----
+    float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f}, dv1[4] = {0.f, 0.f, 0.f, 0.f}, dv2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {
+        const float4 U1 = ld4(sin + ST_U1 * ks + o), U2 = ld4(sin + ST_U2 * ks + o);
+        const float4 IX = ld4(a.Ix + off + o), IY = ld4(a.Iy + off + o);
+        const float4 C0 = ld4((DATA == DATA_TVL1 ? a.rho_c : a.scale) + off + o);
+        const float ix[4] = {IX.x, IX.y, IX.z, IX.w}, iy[4] = {IY.x, IY.y, IY.z, IY.w}, cc[4] = {C0.x, C0.y, C0.z, C0.w};
+        u1[0] = U1.x, u1[1] = U1.y, u1[2] = U1.z, u1[3] = U1.w;
+        u2[0] = U2.x, u2[1] = U2.y, u2[2] = U2.z, u2[3] = U2.w;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float v1, v2;
+            if (DATA == DATA_TVL1) {
+                const float grad = ix[i] * ix[i] + iy[i] * iy[i];
+                const float rho = cc[i] + (ix[i] * u1[i] + iy[i] * u2[i]);
+                float e1, e2;
+                if (rho < -l_t * grad) {
+                    e1 = l_t * ix[i];
+                    e2 = l_t * iy[i];
+                } else if (rho > l_t * grad) {
+                    e1 = -l_t * ix[i];
+                    e2 = -l_t * iy[i];
+                } else if (grad_is_zero(grad)) {
+                    e1 = e2 = 0.f;
+                } else {
+                    const float fi = -rho / grad;
+                    e1 = fi * ix[i];
+                    e2 = fi * iy[i];
+                }
+                v1 = u1[i] + e1;
+                v2 = u2[i] + e2;
+            } else {
+                v1 = u1[i];
+                v2 = u2[i];
+                if (gx0 + i < w && cc[i] != 0.f) {  // 0 marks grad <= GRAD_IS_ZERO (:1734)
+                    const float s = (ix[i] * u1[i] + iy[i] * u2[i]) / cc[i];
+                    const float med = csad_select(a.blk, a.sep, a.g, b, y, gx0 + i, csad_count(gx0 + i, y, w, h), s, l_t, cc[i]);
+                    v1 = u1[i] - ix[i] * med / cc[i];
+                    v2 = u2[i] - iy[i] * med / cc[i];
+                }
+            }
+            dv1[i] = div_const(u1[i] - v1, a.dth);
+            dv2[i] = div_const(u2[i] - v2, a.dth);
+        }
+    }
+
+    // ---- apron planes: own ubar and 1/wt ----
+    mbar_wait(&S.cbar, 0);
+    const int ac = (r + 2) * NLT_PW + 4 + 4 * lane;  // this quad in the apron tiles
+    const float4 C1 = *reinterpret_cast<const float4 *>(&S.ub[0][ac]), C2 = *reinterpret_cast<const float4 *>(&S.ub[1][ac]);
+    const float4 RW = *reinterpret_cast<const float4 *>(&S.rw[ac]);
+    const float c1[4] = {C1.x, C1.y, C1.z, C1.w}, c2[4] = {C2.x, C2.y, C2.z, C2.w}, rwp[4] = {RW.x, RW.y, RW.z, RW.w};
+    float dP[4] = {0.f, 0.f, 0.f, 0.f}, dQ[4] = {0.f, 0.f, 0.f, 0.f};
+
+    // ---- the 24 slots: dual update + non-local divergence ----
+#pragma unroll
+    for (int s = 0; s < NL_SLOTS; s++) {
+        const int sg = s % NLT_NS;
+        int k, l;
+        nl_slot_offset(s, k, l);
+        mbar_wait(&S.full[sg], (s / NLT_NS) & 1);
+        if (act) {
+            const int tc = r * NLT_W + 4 * lane;
+            const float4 W4 = *reinterpret_cast<const float4 *>(&S.own[sg][0][tc]);
+            const float4 P4 = *reinterpret_cast<const float4 *>(&S.own[sg][1][tc]);
+            const float4 Q4 = *reinterpret_cast<const float4 *>(&S.own[sg][2][tc]);
+            const float wv[4] = {W4.x, W4.y, W4.z, W4.w}, po[4] = {P4.x, P4.y, P4.z, P4.w}, qo[4] = {Q4.x, Q4.y, Q4.z, Q4.w};
+            float pr[4], qr[4];
+            nl_shifted4(&S.rec[sg][0][r * NLT_PW + 4 + 4 * lane], l, pr);
+            nl_shifted4(&S.rec[sg][1][r * NLT_PW + 4 + 4 * lane], l, qr);
+            const int nc = ac + k * NLT_PW;  // the quad's column, neighbour row, in the apron tiles
+            float nq1[4], nq2[4], nrw[4];
+            nl_shifted4(&S.ub[0][nc], l, nq1);
+            nl_shifted4(&S.ub[1][nc], l, nq2);
+            nl_shifted4(&S.rw[nc], l, nrw);
+            float pn[4], qn[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                // wgt holds -2 where the neighbour is outside the frame (nltv_init_kernel) and 0 in the pitch
+                // padding: clamping at 0 makes such a slot contribute nothing and leave its (zero) dual
+                // unchanged, with no per-slot bounds tests.  Everything read for it is finite (zero fill).
+                const float wm = fmaxf(wv[i], 0.f);
+                const float q1 = nq1[i], q2 = nq2[i], rwq = nrw[i];
+                const float t1 = wm * (c1[i] - q1), t2 = wm * (c2[i] - q2);
+                // own dual, slot s
+                const float g1 = t1 * rwp[i], g2 = t2 * rwp[i];
+                pn[i] = NL_DIV(po[i] + tau * g1, 1 + tau * fabsf(g1));
+                qn[i] = NL_DIV(qo[i] + tau * g2, 1 + tau * fabsf(g2));
+                // neighbour's reciprocal dual, slot 23-s at q (its difference is the negated one)
+                const float h1 = -t1 * rwq, h2 = -t2 * rwq;
+                const float Pr = NL_DIV(pr[i] + tau * h1, 1 + tau * fabsf(h1));
+                const float Qr = NL_DIV(qr[i] + tau * h2, 1 + tau * fabsf(h2));
+                dP[i] += wm * (pn[i] - Pr);
+                dQ[i] += wm * (qn[i] - Qr);
+            }
+            st4(dout + (size_t)s * ks + o, make_float4(pn[0], pn[1], pn[2], pn[3]));
+            st4(dout + (size_t)(NL_SLOTS + s) * ks + o, make_float4(qn[0], qn[1], qn[2], qn[3]));
+        }
+        if (s + NLT_NS < NL_SLOTS) {
+            __syncthreads();  // everyone is done with this stage's buffers
+            if (tid == 0) issue(s + NLT_NS);
+        }
+    }
+
+    // ---- primal step (+div) and extrapolation ----
+    double esum = 0.0;
+    if (act) {
+        float o1[4], o2[4], b1[4], b2[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            o1[i] = u1[i] - tau * (dP[i] * rwp[i] + dv1[i]);
+            o2[i] = u2[i] - tau * (dQ[i] * rwp[i] + dv2[i]);
+            if (gx0 + i < w) esum += (double)((o1[i] - u1[i]) * (o1[i] - u1[i]) + (o2[i] - u2[i]) * (o2[i] - u2[i]));
+            b1[i] = 2 * o1[i] - u1[i];
+            b2[i] = 2 * o2[i] - u2[i];
+        }
+        st4(sout + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
+        st4(sout + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        st4(sout + ST_UB1 * ks + o, make_float4(b1[0], b1[1], b1[2], b1[3]));
+        st4(sout + ST_UB2 * ks + o, make_float4(b2[0], b2[1], b2[2], b2[3]));
+    }
+    // printed error only (the exit test is commented out upstream, :1248)
+    esum = warp_sum(esum);
+    if (lane == 0) S.red[r] = esum;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLT_H; i++) t += S.red[i];
+        atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
+    }
+}
+
+}  // namespace faldoi

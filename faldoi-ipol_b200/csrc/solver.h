@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "tv_tile_kernel.cuh"
 #include "tv_tile2_kernel.cuh"
+#include "nltv_tile_kernel.cuh"
 
 namespace faldoi {
 
@@ -48,7 +49,8 @@ struct faldoi_solver {
     unsigned char *t2_stat = nullptr;    // [B][t2_stride] launch status of the two-iteration kernel
     int t2_stride = 0;
     // NLTV: Lab, weights, duals
-    float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *dual = nullptr;
+    float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *rwt = nullptr, *dual = nullptr;
+    faldoi::NlTileMaps nlmaps{};  // TMA descriptors of nltv_tile_kernel
     size_t dual_set_stride = 0;
     // device-side preprocessing (upload_raw): staging for the raw frames, scratch planes, min/max keys
     float *raw_stage = nullptr;
