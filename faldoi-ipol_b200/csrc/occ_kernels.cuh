@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_xi_rows_kernel(OccA
     const int cx = 4 * lane;
     const size_t ks = (size_t)a.g.B * a.g.plane;
     const float theta = a.theta, tt = a.tau_theta;
-    const bool in = gy >= 0 && gy < h && gx0 >= 0 && gx0 < pitch;
+    const bool rowin = gy >= 0 && gy < h;
+    const bool in = rowin && gx0 >= 0 && gx0 < pitch;
     const size_t p = (size_t)gy * pitch + gx0;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *xin = occ_plane(a, src ? OC_XI1 : OC_XI0, b);
@@ -561,16 +562,24 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_xi_rows_kernel(OccA
         q2a(r > 0 ? *reinterpret_cast<const float4 *>(&sB[0][r - 1][cx]) : z4, ub1);
         q2a(r > 0 ? *reinterpret_cast<const float4 *>(&sB[1][r - 1][cx]) : z4, ub2);
         const float la1 = __shfl_up_sync(0xffffffffu, a1[3], 1), la2 = __shfl_up_sync(0xffffffffu, a2[3], 1);
-        float vi1[4], vi2[4];
+        // Temporal blocking shrinks the region that still matters by one row per sweep (a trapezoid):
+        // after sweep s only rows s+1 .. ROWS-2-s hold values the tile's result depends on, so whole
+        // warps (warp = row) skip the arithmetic of the other rows and of rows outside the frame.
+        const bool row_vi = rowin && r > s && r < ROWS - s;
+        const bool row_x = rowin && r > s && r < ROWS - 1 - s;
+        float vi1[4] = {0.f, 0.f, 0.f, 0.f}, vi2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_vi) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gx = gx0 + k;
-            vi1[k] = v1[k] + theta * div_bc(a1[k], k ? a1[k - 1] : la1, b1[k], ub1[k], gx, gy, w, h) + k1[k];
-            vi2[k] = v2[k] + theta * div_bc(a2[k], k ? a2[k - 1] : la2, b2[k], ub2[k], gx, gy, w, h) + k2[k];
+            for (int k = 0; k < 4; k++) {
+                const int gx = gx0 + k;
+                vi1[k] = v1[k] + theta * div_bc(a1[k], k ? a1[k - 1] : la1, b1[k], ub1[k], gx, gy, w, h) + k1[k];
+                vi2[k] = v2[k] + theta * div_bc(a2[k], k ? a2[k - 1] : la2, b2[k], ub2[k], gx, gy, w, h) + k2[k];
+            }
+            *reinterpret_cast<float4 *>(&sV[0][r][cx]) = a2q(vi1);
+            *reinterpret_cast<float4 *>(&sV[1][r][cx]) = a2q(vi2);
         }
-        *reinterpret_cast<float4 *>(&sV[0][r][cx]) = a2q(vi1);
-        *reinterpret_cast<float4 *>(&sV[1][r][cx]) = a2q(vi2);
         __syncthreads();
+        if (!row_x) continue;  // (warp-uniform; the barriers of the next sweep are still reached)
         float dn1[4], dn2[4];
         q2a(r < ROWS - 1 ? *reinterpret_cast<const float4 *>(&sV[0][r + 1][cx]) : z4, dn1);
         q2a(r < ROWS - 1 ? *reinterpret_cast<const float4 *>(&sV[1][r + 1][cx]) : z4, dn2);
@@ -623,7 +632,8 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_chi_rows_kernel(Occ
     const int cx = 4 * lane;
     const size_t ks = (size_t)a.g.B * a.g.plane;
     const float mte = a.mu * a.tau_eta;
-    const bool in = gy >= 0 && gy < h && gx0 >= 0 && gx0 < pitch;
+    const bool rowin = gy >= 0 && gy < h;
+    const bool in = rowin && gx0 >= 0 && gx0 < pitch;
     const size_t p = (size_t)gy * pitch + gx0;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *e_in = occ_plane(a, src ? OC_ETA1 : OC_ETA0, b);
@@ -642,9 +652,13 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_chi_rows_kernel(Occ
         float dn[4];
         q2a(r < ROWS - 1 ? *reinterpret_cast<const float4 *>(&sC[r + 1][cx]) : z4, dn);
         const float rc = __shfl_down_sync(0xffffffffu, c[0], 1);
-        float ge1[4], ge2[4];
+        // trapezoid (see occ_xi_rows_kernel): eta matters on rows s .. ROWS-2-s, chi on s+1 .. ROWS-2-s
+        const bool row_e = rowin && r >= s && r < ROWS - 1 - s;
+        const bool row_c = rowin && r > s && r < ROWS - 1 - s;
+        float ge1[4] = {0.f, 0.f, 0.f, 0.f}, ge2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
+            if (!row_e) break;
             const int gx = gx0 + k;
             const float chix = (gx < w - 1) ? (k < 3 ? c[k + 1] : rc) - c[k] : 0.f;
             const float chiy = (gy < h - 1) ? dn[k] - c[k] : 0.f;
@@ -663,6 +677,7 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_chi_rows_kernel(Occ
         }
         *reinterpret_cast<float4 *>(&sE[r][cx]) = a2q(ge2);
         __syncthreads();
+        if (!row_c) continue;  // (warp-uniform)
         float up[4];
         q2a(r > 0 ? *reinterpret_cast<const float4 *>(&sE[r - 1][cx]) : z4, up);
         const float le = __shfl_up_sync(0xffffffffu, ge1[3], 1);
