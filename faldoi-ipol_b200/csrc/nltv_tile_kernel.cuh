@@ -4,7 +4,7 @@
 // The per-pixel kernel issues ~190 scattered plane loads per pixel and iteration and spends its time
 // on the scoreboard (ncu: 10 of 15.7 cycles per issued instruction are long-scoreboard stalls, 3000
 // instructions per pixel, a third of them address arithmetic).  Here one CTA owns a 128 x 8 pixel tile
-// of one pair (warp = row, lane = 4-pixel quad) and walks the 24 neighbour slots through a 3-stage
+// of one pair (warp = row, lane = 4-pixel quad) and walks the 24 neighbour slots through a 4-stage
 // ring of shared-memory buffers filled by TMA box loads:
 //   per slot s, offset (k,l):   wgt[s], P[s], Q[s]         128 x 8 box at (x0,   y0)    -- own
 //                               P[23-s], Q[23-s]           136 x 8 box at (x0-4, y0+k)  -- the neighbour's
@@ -14,7 +14,7 @@
 //                                                          16-byte boundary of global memory: an odd
 //                                                          x origin raises "illegal instruction")
 //   once per tile:              ubar1, ubar2, 1/wt         (128+8) x (8+4) apron boxes
-// Loads of slot s+1, s+2 are in flight while slot s is computed; out-of-frame parts of a box are
+// Loads of the next three slots are in flight while slot s is computed; out-of-frame parts of a box are
 // zero-filled by the TMA unit; slots whose neighbour is outside the frame carry a negative weight and
 // are clamped to zero weight, which is the reference's neighbour-in-image test.
 // New duals go straight to HBM as float4.  Algorithmic traffic is unchanged (532 B / pixel / iteration);
@@ -26,7 +26,7 @@
 namespace faldoi {
 
 #ifndef FALDOI_NLT_STAGES
-#define FALDOI_NLT_STAGES 3
+#define FALDOI_NLT_STAGES 4
 #endif
 enum {
     NLT_W = 128,
@@ -71,6 +71,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     }
 }
 
+// Order in which the slots are visited.  Dual plane s is read twice per iteration: as slot s of its own
+// pixel and as the reciprocal of slot 23-s of a neighbour.  Visiting 0, 23, 1, 22, ... puts the two reads
+// one step apart, so the second one is an L2 hit instead of a second trip to HBM (the planes of a
+// batch are far larger than L2, and in ascending order the reuse distance is up to 23 steps).
+// The non-local divergence is then summed in that order; the NLTV models are tolerance-level, and
+// FALDOI_NLT_PAIRED=0 restores the reference's ascending order.
+#ifndef FALDOI_NLT_PAIRED
+#define FALDOI_NLT_PAIRED 1
+#endif
+__host__ __device__ constexpr int nl_step_slot(int step) {
+    return FALDOI_NLT_PAIRED ? ((step & 1) ? NL_SLOTS - 1 - (step >> 1) : (step >> 1)) : step;
+}
+
 // out[i] = row[i + l], l in -2..2 known at compile time after unrolling: two aligned float4 loads and a
 // static pick instead of four scalar loads (which would be 4-way bank conflicts at a lane stride of 4)
 __device__ __forceinline__ void nl_shifted4(const float *row, int l, float (&out)[4]) {
@@ -101,8 +114,8 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
     const int zd = par * 2 * NL_SLOTS * B + b;  // plane index of dual slot 0 of this pair in the input set
     const int zs = par * ST_COUNT * B + b;
 
-    auto issue = [&](int s) {  // one thread: arm the stage's barrier and start its five box loads
-        const int sg = s % NLT_NS, rs = NL_SLOTS - 1 - s;
+    auto issue = [&](int step) {  // one thread: arm the stage's barrier and start its five box loads
+        const int sg = step % NLT_NS, s = nl_step_slot(step), rs = NL_SLOTS - 1 - s;
         int k, l;
         nl_slot_offset(s, k, l);
         (void)l;
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
         tma_box(S.ub[1], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB2 * B, &S.cbar);
         tma_box(S.rw, &maps.rwt, x0 - 4, y0 - 2, b, &S.cbar);
 #pragma unroll
-        for (int s = 0; s < NLT_NS; s++) issue(s);
+        for (int step = 0; step < NLT_NS; step++) issue(step);
     }
     __syncthreads();  // barrier objects are initialised for everyone
 
@@ -192,11 +205,11 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
 
     // ---- the 24 slots: dual update + non-local divergence ----
 #pragma unroll
-    for (int s = 0; s < NL_SLOTS; s++) {
-        const int sg = s % NLT_NS;
+    for (int step = 0; step < NL_SLOTS; step++) {
+        const int sg = step % NLT_NS, s = nl_step_slot(step);
         int k, l;
         nl_slot_offset(s, k, l);
-        mbar_wait(&S.full[sg], (s / NLT_NS) & 1);
+        mbar_wait(&S.full[sg], (step / NLT_NS) & 1);
         if (act) {
             const int tc = r * NLT_W + 4 * lane;
             const float4 W4 = *reinterpret_cast<const float4 *>(&S.own[sg][0][tc]);
@@ -234,9 +247,9 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
             st4(dout + (size_t)s * ks + o, make_float4(pn[0], pn[1], pn[2], pn[3]));
             st4(dout + (size_t)(NL_SLOTS + s) * ks + o, make_float4(qn[0], qn[1], qn[2], qn[3]));
         }
-        if (s + NLT_NS < NL_SLOTS) {
+        if (step + NLT_NS < NL_SLOTS) {
             __syncthreads();  // everyone is done with this stage's buffers
-            if (tid == 0) issue(s + NLT_NS);
+            if (tid == 0) issue(step + NLT_NS);
         }
     }
 
