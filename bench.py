@@ -331,8 +331,8 @@ def main():
                          "pairs_per_s": world * B * a.steps / t_e2e},
                     pairs_per_s=world * B * a.steps / t_res, iters_per_pair=iters_total / B,
                     gpu_launches=int(launches_all),
-                    roofline={"bound": "hbm", "kernel": {0: "tv_tile2_kernel", 1: "tv_tile2_kernel", 4: "tv_tile_kernel<CSAD>", 5: "tv_tile_kernel<CSAD>", 2: "nltv_iter_kernel", 3: "nltv_iter_kernel",
-                                         6: "nltv_iter_kernel<CSAD>", 7: "nltv_iter_kernel<CSAD>", 8: "occ_xi_rows_kernel + occ_chi_rows_kernel"}[method],
+                    roofline={"bound": "hbm", "kernel": {0: "tv_tile2_kernel", 1: "tv_tile2_kernel", 4: "tv_tile_kernel<CSAD>", 5: "tv_tile_kernel<CSAD>", 2: "nltv_tile_kernel", 3: "nltv_tile_kernel",
+                                         6: "nltv_tile_kernel<CSAD>", 7: "nltv_tile_kernel<CSAD>", 8: "occ_xi_rows_kernel + occ_chi_rows_kernel"}[method],
                               "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                               "alg_bytes_per_px_iter": alg, "traffic": traffic},
                     clocks=clocks)
