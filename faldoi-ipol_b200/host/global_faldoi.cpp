@@ -7,13 +7,16 @@
 // minimisation itself (tvl2OF / nltvl1_PD / tvcsad_PD / nltvcsad_PD /
 // guided_tvl2coupled_occ) runs on a B200 through the C ABI in include/faldoi_gpu.h.
 // Extra options (unknown to the reference's scripts): -device d (CUDA device, default 0),
-// -host_preproc 1 (run main()'s preprocessing on the host instead of the GPU).
+// -host_preproc 1 (run main()'s preprocessing on the host instead of the GPU), -seq jobs.txt
+// (many pairs in one process; files of job k+1 are read and decoded and the results of job k-1
+// are written by host threads while job k is on the GPU -- SURVEY 8f rows 3 and 4).
 // There is no CPU fallback: without a usable GPU the program reports the error and fails.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
@@ -80,42 +83,87 @@ struct Options {
     std::string file_params;
 };
 
-// one invocation of the reference executable: positional = {argv0, ims.txt, in.flo, out.flo[, occ_in, occ_out]}
-static int run_pair(const std::vector<std::string> &args, const Options &opt) {
+// Stage 1 of a job (host I/O, no messages): ims.txt + the frames, the flow and the occlusion
+// mask, decoded concurrently.  Errors are kept for the solve stage to report in job order.
+struct Loaded {
+    Image i_1, i0, i1, flow, occ;
+    int num_files = 0;
+    std::exception_ptr err;
+};
+
+static Loaded load_inputs(const std::vector<std::string> &args, int val_method) {
+    Loaded L;
+    try {
+        // ims.txt: line 1 = I0, line 2 = I1, line 3 = I-1, line 4 = I2 (unused)
+        std::string filename_i_1, filename_i0, filename_i1, line;
+        {
+            std::ifstream infile(args[1]);
+            while (std::getline(infile, line)) {
+                ++L.num_files;
+                if (L.num_files == 1) filename_i0 = line;
+                if (L.num_files == 2) filename_i1 = line;
+                if (L.num_files == 3) filename_i_1 = line;
+            }
+        }
+        // with fewer than 4 lines the reference reads I1 in place of I-1 (:1933-1937)
+        const std::string third = (L.num_files == 4) ? filename_i_1 : filename_i1;
+        auto rd = [](std::string f) { return faldoi_host::read_image_split(f); };
+        std::future<Image> f0 = std::async(std::launch::async, rd, filename_i0);
+        std::future<Image> f1 = std::async(std::launch::async, rd, filename_i1);
+        std::future<Image> ff = std::async(std::launch::async, rd, args[2]);
+        std::future<Image> fo;
+        if (val_method >= 8) fo = std::async(std::launch::async, rd, args.size() == 6 ? args[4] : std::string());
+        std::exception_ptr first;
+        auto take = [&](std::future<Image> &f, Image &dst) {
+            try {
+                dst = f.get();
+            } catch (...) {
+                if (!first) first = std::current_exception();
+            }
+        };
+        try {  // same order as the reference reads them, so the same file is blamed first
+            L.i_1 = rd(third);
+        } catch (...) {
+            first = std::current_exception();
+        }
+        take(f0, L.i0);
+        take(f1, L.i1);
+        take(ff, L.flow);
+        if (val_method >= 8) take(fo, L.occ);
+        L.err = first;
+    } catch (...) {
+        L.err = std::current_exception();
+    }
+    return L;
+}
+
+// Stage 3 of a job: the output files.
+struct Outputs {
+    std::string flow_file, occ_file;
+    std::vector<float> u;
+    std::vector<int> occ;
+    int w = 0, h = 0;
+};
+static void save_outputs(const Outputs &o) {
+    faldoi_host::write_image_float_split(o.flow_file, o.u.data(), o.w, o.h, 2);
+    if (!o.occ_file.empty()) faldoi_host::write_png_gray8(o.occ_file, o.occ.data(), o.w, o.h);
+}
+
+// one invocation of the reference executable: positional = {argv0, ims.txt, in.flo, out.flo[, occ_in, occ_out]}.
+// `writer` (sequence mode): the files are written by a host thread while the next job is solved.
+static int run_pair(const std::vector<std::string> &args, const Options &opt, Loaded &in, std::future<void> *writer) {
     int val_method = opt.val_method;
     const int nwarps = opt.nwarps, glb_it = opt.glb_it, device = opt.device;
     const bool verbose = opt.verbose, host_preproc = opt.host_preproc;
     const std::string &file_params = opt.file_params;
-    const std::string &filename_images = args[1];
-    const std::string &image_flow_name = args[2];
     const std::string &outfile = args[3];
-    std::string occ_input, occ_output;
-    if (args.size() == 6) {
-        occ_input = args[4];
-        occ_output = args[5];
-    }
-
-    // ims.txt: line 1 = I0, line 2 = I1, line 3 = I-1, line 4 = I2 (unused)
-    std::string filename_i_1, filename_i0, filename_i1, line;
-    int num_files = 0;
-    {
-        std::ifstream infile(filename_images);
-        while (std::getline(infile, line)) {
-            ++num_files;
-            if (num_files == 1) filename_i0 = line;
-            if (num_files == 2) filename_i1 = line;
-            if (num_files == 3) filename_i_1 = line;
-        }
-    }
+    std::string occ_output;
+    if (args.size() == 6) occ_output = args[5];
+    const int num_files = in.num_files;
 
     try {
-        // with fewer than 4 lines the reference reads I1 in place of I-1 (:1933-1937)
-        const Image i_1 = faldoi_host::read_image_split(num_files == 4 ? filename_i_1 : filename_i1);
-        const Image i0 = faldoi_host::read_image_split(filename_i0);
-        const Image i1 = faldoi_host::read_image_split(filename_i1);
-        const Image flow = faldoi_host::read_image_split(image_flow_name);
-        Image occ;
-        if (val_method >= 8) occ = faldoi_host::read_image_split(occ_input);
+        if (in.err) std::rethrow_exception(in.err);
+        const Image &i_1 = in.i_1, &i0 = in.i0, &i1 = in.i1, &flow = in.flow, &occ = in.occ;
 
         auto same = [](const Image &a, const Image &b) { return a.w == b.w && a.h == b.h && a.pd == b.pd; };
         if (num_files == 3) {
@@ -169,7 +217,7 @@ static int run_pair(const std::vector<std::string> &args, const Options &opt) {
             return EXIT_FAILURE;
         }
 
-        std::vector<float> u(flow.data);  // u1 | u2
+        std::vector<float> u(std::move(in.flow.data));  // u1 | u2
         std::vector<float> chi;
         if (val_method >= 8) chi.assign(occ.data.begin(), occ.data.begin() + size);
 
@@ -213,11 +261,20 @@ static int run_pair(const std::vector<std::string> &args, const Options &opt) {
         if (val_method == FALDOI_M_TVL1 || val_method == FALDOI_M_TVL1_W) std::cout << "(tvl2OF) All tasks took " << secs.count() << std::endl;
         if (val_method == FALDOI_M_TVCSAD || val_method == FALDOI_M_TVCSAD_W) std::printf("Exits current level\n");
 
-        faldoi_host::write_image_float_split(outfile, u.data(), w, h, 2);
+        Outputs out;
+        out.flow_file = outfile;
+        out.u = std::move(u);
+        out.w = w, out.h = h;
         if (val_method == FALDOI_M_TVL1_OCC) {
-            std::vector<int> out_occ(size);
-            for (size_t i = 0; i < size; i++) out_occ[i] = (int)chi[i];
-            faldoi_host::write_png_gray8(occ_output, out_occ.data(), w, h);
+            out.occ_file = occ_output;
+            out.occ.resize(size);
+            for (size_t i = 0; i < size; i++) out.occ[i] = (int)chi[i];
+        }
+        if (writer) {
+            if (writer->valid()) writer->get();  // at most one job's files in flight; its errors surface here
+            *writer = std::async(std::launch::async, [o = std::move(out)]() { save_outputs(o); });
+        } else {
+            save_outputs(out);
         }
     } catch (const std::exception &e) {
         fprintf(stderr, "ERROR: %s\n", e.what());
@@ -264,7 +321,8 @@ int main(int argc, char *argv[]) {
 
     int rc = EXIT_SUCCESS;
     if (seq_file.empty()) {
-        rc = run_pair(args, opt);
+        Loaded in = load_inputs(args, opt.val_method);
+        rc = run_pair(args, opt, in, nullptr);
     } else {
         std::ifstream jobs(seq_file);
         if (!jobs) {
@@ -272,19 +330,39 @@ int main(int argc, char *argv[]) {
             return EXIT_FAILURE;
         }
         std::string line;
-        int njobs = 0;
+        std::vector<std::vector<std::string>> joblist;
         while (std::getline(jobs, line)) {
             std::vector<std::string> job{args[0]};
             std::string tok;
             for (std::istringstream ls(line); ls >> tok;) job.push_back(tok);
             if (job.size() == 1) continue;
             if (job.size() != 4 && job.size() != 6) {
-                fprintf(stderr, "ERROR: job %d of '%s' needs 3 or 5 file names\n", njobs + 1, seq_file.c_str());
+                fprintf(stderr, "ERROR: job %d of '%s' needs 3 or 5 file names\n", (int)joblist.size() + 1, seq_file.c_str());
                 return EXIT_FAILURE;
             }
-            const int r = run_pair(job, opt);
-            if (r != EXIT_SUCCESS) return r;
+            joblist.push_back(job);
+        }
+        // three-stage pipeline: load k+1 | solve k (this thread, GPU) | save k-1
+        int njobs = 0;
+        std::future<void> writer;
+        std::future<Loaded> next;
+        if (!joblist.empty()) next = std::async(std::launch::async, load_inputs, joblist[0], opt.val_method);
+        for (size_t k = 0; k < joblist.size(); k++) {
+            Loaded in = next.get();
+            if (k + 1 < joblist.size()) next = std::async(std::launch::async, load_inputs, joblist[k + 1], opt.val_method);
+            const int r = run_pair(joblist[k], opt, in, &writer);
+            if (r != EXIT_SUCCESS) {
+                if (next.valid()) next.wait();
+                if (writer.valid()) writer.wait();
+                return r;
+            }
             njobs++;
+        }
+        try {
+            if (writer.valid()) writer.get();
+        } catch (const std::exception &e) {
+            fprintf(stderr, "ERROR: %s\n", e.what());
+            return EXIT_FAILURE;
         }
         fprintf(stderr, "sequence: %d pairs done\n", njobs);
     }

@@ -199,3 +199,32 @@ def test_cli_sequence_mode(H, tmp_path, po):
     assert "sequence: 3 pairs done" in r.stderr
     for o in outs:
         assert np.array_equal(po.read_flo(o), g["u_m0_w3"])
+
+
+@pytest.mark.gpu
+def test_cli_sequence_pipeline_occ_and_errors(H, tmp_path, po):
+    """-seq with method 8 (flow + occlusion PNG per job, written by the background writer) and a job whose
+    input is missing: the run stops with a non-zero code, the jobs before it are complete on disk."""
+    from PIL import Image
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po)
+    Image.fromarray(g["chi0"].astype(np.uint8)).save(tmp_path / "occ_in.png")
+    occ_in = str(tmp_path / "occ_in.png")
+    jobs = ["%s %s %s %s %s" % (ims, flo, tmp_path / ("o%d.flo" % k), occ_in, tmp_path / ("m%d.png" % k)) for k in range(4)]
+    (tmp_path / "jobs.txt").write_text("\n".join(jobs) + "\n")
+    opts = ["-m", "8", "-w", "1", "-glb_iters", "12"]
+    r = subprocess.run([BIN, "-seq", str(tmp_path / "jobs.txt")] + opts, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "sequence: 4 pairs done" in r.stderr
+    for k in range(4):
+        assert np.array_equal(po.read_flo(str(tmp_path / ("o%d.flo" % k))), g["u_m8_w1_i12"])
+        assert np.array_equal(np.asarray(Image.open(tmp_path / ("m%d.png" % k))).astype(np.float32), g["chi_m8_w1_i12"])
+    # job 2 of 3 points at a flow file that does not exist
+    bad = [jobs[0].replace("o0.flo", "p0.flo").replace("m0.png", "q0.png"),
+           "%s %s %s %s %s" % (ims, tmp_path / "nope.flo", tmp_path / "p1.flo", occ_in, tmp_path / "q1.png"),
+           jobs[2].replace("o2.flo", "p2.flo").replace("m2.png", "q2.png")]
+    (tmp_path / "bad.txt").write_text("\n".join(bad) + "\n")
+    r = subprocess.run([BIN, "-seq", str(tmp_path / "bad.txt")] + opts, capture_output=True, text=True)
+    assert r.returncode != 0 and "ERROR" in r.stderr
+    assert np.array_equal(po.read_flo(str(tmp_path / "p0.flo")), g["u_m8_w1_i12"])
+    assert not os.path.exists(tmp_path / "p1.flo") and not os.path.exists(tmp_path / "p2.flo")
