@@ -26,8 +26,16 @@ namespace faldoi {
 // owns one staged row and a lane owns one quad -- no index arithmetic, row tests are warp-uniform,
 // and every phase is a single balanced round: 11 / 10 / 9 / 8 busy warps of the CTA's 11.  The tile
 // written back is the inner 120 x 8 pixels (quads 1..30).
+// FALDOI_T2_H / FALDOI_T2_CTAS: tile rows and resident CTAs per SM (8 rows, 11 warps, 60 KB -> 3 CTAs;
+// taller tiles recompute relatively less apron but hold fewer, larger CTAs -- profiles/README.md)
+#ifndef FALDOI_T2_H
+#define FALDOI_T2_H 8
+#endif
+#ifndef FALDOI_T2_CTAS
+#define FALDOI_T2_CTAS 3
+#endif
 enum {
-    T2_H = 8,                 // tile rows
+    T2_H = FALDOI_T2_H,       // tile rows
     T2_W = 120,               // tile columns written by a CTA
     T2_PW = 128,              // staged columns
     T2_QUADS = T2_PW / 4,     // 32
@@ -228,7 +236,7 @@ struct T2Args {
     int stat_stride;
 };
 
-__global__ void __launch_bounds__(T2_THREADS, 3) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
+__global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
     // (no pointer arithmetic on the base: it would demote every access from LDS/STS to generic LD/ST)
     extern __shared__ __align__(1024) unsigned char smem_raw2[];
     Tile2Smem &S = *reinterpret_cast<Tile2Smem *>(smem_raw2);
