@@ -313,7 +313,8 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
             make_plane_map(&s->nlmaps.rec, s->dual, s->g, (size_t)4 * NL_SLOTS * B, NLT_PW, NLT_H) ||
             make_plane_map(&s->nlmaps.wgt, s->wgt, s->g, (size_t)NL_SLOTS * B, NLT_W, NLT_H) ||
             make_plane_map(&s->nlmaps.ub, s->state, s->g, (size_t)2 * ST_COUNT * B, NLT_PW, NLT_AR) ||
-            make_plane_map(&s->nlmaps.rwt, s->rwt, s->g, B, NLT_PW, NLT_AR))
+            make_plane_map(&s->nlmaps.rwt, s->rwt, s->g, B, NLT_PW, NLT_AR) ||
+            make_plane_map(&s->nlmaps.wt, s->wt, s->g, B, NLT_PW, NLT_AR))
             return fail(FALDOI_ERR_CUDA);
     }
     if (fam == FAM_OCC) {
@@ -327,9 +328,13 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(tv_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
                  "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
+        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_TVL1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
                  "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
+        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_CSAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
+                 "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_TVL1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
+                 "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_CSAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
                  "cudaFuncSetAttribute"))
         return fail(FALDOI_ERR_CUDA);
     if (!cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize")) return fail(FALDOI_ERR_CUDA);
@@ -861,16 +866,24 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
-        // FALDOI_NLTV_KERNEL=simple selects the first version (one thread per pixel, plain loads)
+        // Default: tiled kernel, exact arithmetic (bit-identical to the reference).  FALDOI_NLTV_FAST=1: tiled kernel
+        // with approximate divisions and paired slot order; FALDOI_NLTV_KERNEL=simple: the first version (one
+        // thread per pixel, plain loads, approximate divisions).
         static const bool tiled = !(getenv("FALDOI_NLTV_KERNEL") && !strcmp(getenv("FALDOI_NLTV_KERNEL"), "simple"));
+        const bool fast = getenv("FALDOI_NLTV_FAST") && atoi(getenv("FALDOI_NLTV_FAST")) != 0;  // read per run
         const dim3 tgrid((g.pitch + NLT_W - 1) / NLT_W, (g.h + NLT_H - 1) / NLT_H, npairs);
         const size_t tsm = sizeof(NlTileSmem) + 128;
         for (int it = 0; it < p->max_iters; it++) {
-            if (tiled) {
+            if (tiled && fast) {
                 if (csad)
-                    nltv_tile_kernel<DATA_CSAD><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
+                    nltv_tile_kernel<DATA_CSAD, false><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
                 else
-                    nltv_tile_kernel<DATA_TVL1><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
+                    nltv_tile_kernel<DATA_TVL1, false><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
+            } else if (tiled) {
+                if (csad)
+                    nltv_tile_kernel<DATA_CSAD, true><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
+                else
+                    nltv_tile_kernel<DATA_TVL1, true><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
             } else if (csad) {
                 nltv_iter_kernel<DATA_CSAD><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
             } else {

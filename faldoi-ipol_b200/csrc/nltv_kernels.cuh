@@ -14,22 +14,21 @@ namespace faldoi {
 
 enum { NL_SLOTS = 24 };
 
-// The NLTV models are held to the north star's fp32 tolerance, not to bit equality (their
-// weights already differ from glibc's expf in the last bit), so the 192 divisions per pixel
-// and iteration of the dual updates are a * rcp.approx(b) (MUFU.RCP + FMUL, 2 ulp).  Every
-// divisor here is 1 + tau*|g| >= 1 or a weight sum, far from the 2^126 range where the approximate
-// reciprocal needs the rescaling that __fdividef wraps around it (2 more FMUL + a compare each).
-// Build with -DFALDOI_NLTV_IEEE_DIV for IEEE division.
+// Two arithmetic modes (chosen at run time, FALDOI_NLTV_FAST=1 selects the second):
+//   exact  every operation of ofnltv_getD / non_local_divergence / ofnltv_getP as the reference writes
+//          it: (w*(u_p-u_q))/wt, (sc + tau*g)/(1 + tau*|g|) and div/wt are IEEE divisions, the 24 terms
+//          of the divergence are summed in ascending slot order.  With the weights below the NLTV
+//          flows are bit-identical to the reference's.
+//   fast   a * rcp.approx(b) (MUFU.RCP + FMUL, 2 ulp) for the 192 divisions per pixel and iteration,
+//          1/wt formed once per pixel, slots visited as (s, 23-s) pairs.  Inside the north star's mean
+//          tolerance; the CSAD variants are chaotic enough (a rank flip moves a pixel by 1e-2 px) that
+//          a few pixels of a full-size frame can exceed its max tolerance, which is why it is opt-in.
 __device__ __forceinline__ float nl_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-#ifdef FALDOI_NLTV_IEEE_DIV
-#define NL_DIV(a, b) ((a) / (b))
-#else
 #define NL_DIV(a, b) ((a) * nl_rcp(b))
-#endif
 
 struct NlOffsets {
     float ws[NL_SLOTS];  // exp(-hypot(l,k)/2) per slot, evaluated on the host with libm (get_wspatial_2 :943-952)
@@ -44,8 +43,7 @@ __host__ __device__ __forceinline__ void nl_slot_offset(int s, int &k, int &l) {
 // ---------------------------------------------------------------------------
 // initialize_dual_variables (:996-1054): wp = sqrt(w_colour * w_spatial),
 // w_colour = exp(-|Lab(p)-Lab(q)|/5) (get_wcolor_2 :954-978), wt = sum of the
-// in-image wp in slot order.  exp() is evaluated in double and rounded to
-// float (the reference calls glibc expf; see DESIGN.md "NLTV weights").
+// in-image wp in slot order.  expf is glibc's algorithm (expf_glibc_nonpositive above).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nltv_init_kernel(const float *__restrict__ lab, float *__restrict__ wgt,
                                                         float *__restrict__ wt, float *__restrict__ rwt, NlOffsets offs, Geo g) {
@@ -73,7 +71,7 @@ __global__ void __launch_bounds__(256) nltv_init_kernel(const float *__restrict_
             aux = Bc - lab[2 * ks + off + q];
             d += aux * aux;
             d = sqrtf(d);
-            const float wc = (float)exp((double)(-d / 5.f));
+            const float wc = expf_glibc_nonpositive(-d / 5.f);
             wv = sqrtf(wc * offs.ws[s]);
             ne += wv;
         }

@@ -55,7 +55,8 @@ struct NlTileMaps {
     CUtensorMap rec;   // same array, box 136 x 8
     CUtensorMap wgt;   // [24][B], box 128 x 8
     CUtensorMap ub;    // state [2 sets][ST_COUNT][B], box 136 x 12
-    CUtensorMap rwt;   // [B], box 136 x 12
+    CUtensorMap rwt;   // [B], box 136 x 12: 1/wt (fast mode)
+    CUtensorMap wt;    // [B], box 136 x 12: wt (exact mode)
 };
 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
@@ -75,13 +76,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // pixel and as the reciprocal of slot 23-s of a neighbour.  Visiting 0, 23, 1, 22, ... puts the two reads
 // one step apart, so the second one is an L2 hit instead of a second trip to HBM (the planes of a
 // batch are far larger than L2, and in ascending order the reuse distance is up to 23 steps).
-// The non-local divergence is then summed in that order; the NLTV models are tolerance-level, and
-// FALDOI_NLT_PAIRED=0 restores the reference's ascending order.
-#ifndef FALDOI_NLT_PAIRED
-#define FALDOI_NLT_PAIRED 1
-#endif
+// The non-local divergence is then summed in that order, so only the fast arithmetic mode does this;
+// the exact mode keeps the reference's ascending order (nltv_kernels.cuh, "Two arithmetic modes").
+template <bool PAIRED>
 __host__ __device__ constexpr int nl_step_slot(int step) {
-    return FALDOI_NLT_PAIRED ? ((step & 1) ? NL_SLOTS - 1 - (step >> 1) : (step >> 1)) : step;
+    return PAIRED ? ((step & 1) ? NL_SLOTS - 1 - (step >> 1) : (step >> 1)) : step;
 }
 
 // out[i] = row[i + l], l in -2..2 known at compile time after unrolling: two aligned float4 loads and a
@@ -103,7 +102,7 @@ __device__ __forceinline__ void nl_shifted4(const float *row, int l, float (&out
     }
 }
 
-template <int DATA>
+template <int DATA, bool EXACT>
 __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_constant__ NlTileMaps maps, NlArgs a, int it, int base_parity) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     NlTileSmem &S = *reinterpret_cast<NlTileSmem *>(smem_raw);
@@ -115,7 +114,7 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
     const int zs = par * ST_COUNT * B + b;
 
     auto issue = [&](int step) {  // one thread: arm the stage's barrier and start its five box loads
-        const int sg = step % NLT_NS, s = nl_step_slot(step), rs = NL_SLOTS - 1 - s;
+        const int sg = step % NLT_NS, s = nl_step_slot<!EXACT>(step), rs = NL_SLOTS - 1 - s;
         int k, l;
         nl_slot_offset(s, k, l);
         (void)l;
@@ -134,7 +133,7 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.cbar)), "r"((unsigned)(3 * NLT_APRON * 4)) : "memory");
         tma_box(S.ub[0], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB1 * B, &S.cbar);
         tma_box(S.ub[1], &maps.ub, x0 - 4, y0 - 2, zs + ST_UB2 * B, &S.cbar);
-        tma_box(S.rw, &maps.rwt, x0 - 4, y0 - 2, b, &S.cbar);
+        tma_box(S.rw, EXACT ? &maps.wt : &maps.rwt, x0 - 4, y0 - 2, b, &S.cbar);
 #pragma unroll
         for (int step = 0; step < NLT_NS; step++) issue(step);
     }
@@ -200,15 +199,21 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
     const int ac = (r + 2) * NLT_PW + 4 + 4 * lane;  // this quad in the apron tiles
     const float4 C1 = *reinterpret_cast<const float4 *>(&S.ub[0][ac]), C2 = *reinterpret_cast<const float4 *>(&S.ub[1][ac]);
     const float4 RW = *reinterpret_cast<const float4 *>(&S.rw[ac]);
-    const float c1[4] = {C1.x, C1.y, C1.z, C1.w}, c2[4] = {C2.x, C2.y, C2.z, C2.w}, rwp[4] = {RW.x, RW.y, RW.z, RW.w};
+    // rwp: 1/wt of the own pixels (fast) or wt itself (exact; 1 in the pitch padding, where wt is 0 and every weight too)
+    const float c1[4] = {C1.x, C1.y, C1.z, C1.w}, c2[4] = {C2.x, C2.y, C2.z, C2.w};
+    float rwp[4] = {RW.x, RW.y, RW.z, RW.w};
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) rwp[i] = rwp[i] > 0.f ? rwp[i] : 1.f;
+    }
     float dP[4] = {0.f, 0.f, 0.f, 0.f}, dQ[4] = {0.f, 0.f, 0.f, 0.f};
 
     // ---- the 24 slots: dual update + non-local divergence ----
-#pragma unroll
-    for (int step = 0; step < NL_SLOTS; step++) {
-        const int sg = step % NLT_NS, s = nl_step_slot(step);
-        int k, l;
-        nl_slot_offset(s, k, l);
+    // The slot loop is rolled over the window rows (5 bodies instead of 24: the fully unrolled exact
+    // version is 280 KB of code and stalls on instruction fetch); the column offset l stays a
+    // compile-time constant of each body because it selects registers in nl_shifted4.
+    auto slot_body = [&](int step, int s, int k, int l) {
+        const int sg = step % NLT_NS;
         mbar_wait(&S.full[sg], (step / NLT_NS) & 1);
         if (act) {
             const int tc = r * NLT_W + 4 * lane;
@@ -231,16 +236,32 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
                 // padding: clamping at 0 makes such a slot contribute nothing and leave its (zero) dual
                 // unchanged, with no per-slot bounds tests.  Everything read for it is finite (zero fill).
                 const float wm = fmaxf(wv[i], 0.f);
-                const float q1 = nq1[i], q2 = nq2[i], rwq = nrw[i];
+                const float q1 = nq1[i], q2 = nq2[i];
                 const float t1 = wm * (c1[i] - q1), t2 = wm * (c2[i] - q2);
-                // own dual, slot s
-                const float g1 = t1 * rwp[i], g2 = t2 * rwp[i];
-                pn[i] = NL_DIV(po[i] + tau * g1, 1 + tau * fabsf(g1));
-                qn[i] = NL_DIV(qo[i] + tau * g2, 1 + tau * fabsf(g2));
-                // neighbour's reciprocal dual, slot 23-s at q (its difference is the negated one)
-                const float h1 = -t1 * rwq, h2 = -t2 * rwq;
-                const float Pr = NL_DIV(pr[i] + tau * h1, 1 + tau * fabsf(h1));
-                const float Qr = NL_DIV(qr[i] + tau * h2, 1 + tau * fabsf(h2));
+                float Pr, Qr;
+                if (EXACT) {
+                    // the reference's operations, one for one (ofnltv_getD :1127-1174): (w*(u_p-u_q))/wt, then
+                    // (sc + tau*g)/(1 + tau*sqrt(g*g)); sqrt(g*g) == |g| whenever g*g is a normal float, and
+                    // below that 1 + tau*(either) rounds to 1.  A slot without neighbour divides by 1, not by
+                    // the zero fill.
+                    const float wq = wm > 0.f ? nrw[i] : 1.f;
+                    const float g1 = t1 / rwp[i], g2 = t2 / rwp[i];
+                    pn[i] = (po[i] + tau * g1) / (1 + tau * fabsf(g1));
+                    qn[i] = (qo[i] + tau * g2) / (1 + tau * fabsf(g2));
+                    const float h1 = -t1 / wq, h2 = -t2 / wq;
+                    Pr = (pr[i] + tau * h1) / (1 + tau * fabsf(h1));
+                    Qr = (qr[i] + tau * h2) / (1 + tau * fabsf(h2));
+                } else {
+                    const float rwq = nrw[i];
+                    // own dual, slot s
+                    const float g1 = t1 * rwp[i], g2 = t2 * rwp[i];
+                    pn[i] = NL_DIV(po[i] + tau * g1, 1 + tau * fabsf(g1));
+                    qn[i] = NL_DIV(qo[i] + tau * g2, 1 + tau * fabsf(g2));
+                    // neighbour's reciprocal dual, slot 23-s at q (its difference is the negated one)
+                    const float h1 = -t1 * rwq, h2 = -t2 * rwq;
+                    Pr = NL_DIV(pr[i] + tau * h1, 1 + tau * fabsf(h1));
+                    Qr = NL_DIV(qr[i] + tau * h2, 1 + tau * fabsf(h2));
+                }
                 dP[i] += wm * (pn[i] - Pr);
                 dQ[i] += wm * (qn[i] - Qr);
             }
@@ -251,6 +272,31 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
             __syncthreads();  // everyone is done with this stage's buffers
             if (tid == 0) issue(step + NLT_NS);
         }
+    };
+    if (EXACT) {  // ascending slots: window rows k = -2..2, columns l = -2..2, centre skipped
+        int step = 0;
+#pragma unroll 1
+        for (int kk = 0; kk < 5; kk++) {
+#pragma unroll
+            for (int ll = 0; ll < 5; ll++) {
+                if (kk == 2 && ll == 2) continue;
+                slot_body(step, step, kk - 2, ll - 2);
+                step++;
+            }
+        }
+    } else {  // pairs (s, 23-s): offsets (k,l) and (-k,-l)
+        int step = 0;
+#pragma unroll 1
+        for (int kk = 0; kk < 3; kk++) {
+#pragma unroll
+            for (int ll = 0; ll < 5; ll++) {
+                if (kk == 2 && ll >= 2) continue;
+                const int sl = kk * 5 + ll;
+                slot_body(step, sl, kk - 2, ll - 2);
+                slot_body(step + 1, NL_SLOTS - 1 - sl, 2 - kk, 2 - ll);
+                step += 2;
+            }
+        }
     }
 
     // ---- primal step (+div) and extrapolation ----
@@ -259,8 +305,9 @@ __global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_
         float o1[4], o2[4], b1[4], b2[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            o1[i] = u1[i] - tau * (dP[i] * rwp[i] + dv1[i]);
-            o2[i] = u2[i] - tau * (dQ[i] * rwp[i] + dv2[i]);
+            const float dp = EXACT ? dP[i] / rwp[i] : dP[i] * rwp[i], dq = EXACT ? dQ[i] / rwp[i] : dQ[i] * rwp[i];
+            o1[i] = u1[i] - tau * (dp + dv1[i]);
+            o2[i] = u2[i] - tau * (dq + dv2[i]);
             if (gx0 + i < w) esum += (double)((o1[i] - u1[i]) * (o1[i] - u1[i]) + (o2[i] - u2[i]) * (o2[i] - u2[i]));
             b1[i] = 2 * o1[i] - u1[i];
             b2[i] = 2 * o2[i] - u2[i];

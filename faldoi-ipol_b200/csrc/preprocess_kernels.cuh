@@ -2,8 +2,9 @@
 // rgb2gray (src/global_faldoi.cpp:1820-1827), image_normalization_3 (src/utils.cpp:743-781),
 // gaussian (src/utils.cpp:521-630) and image_to_lab (src/global_faldoi.cpp:906-932).
 // Gray / normalise / smooth are bit-identical to the host code (same expression types and
-// summation order, no FMA); the Lab conversion uses the device's double pow / exp where the
-// reference calls glibc's, so it is tolerance-level like the NLTV weights it feeds.
+// summation order, no FMA); the Lab conversion uses the device's double pow where the reference calls
+// glibc's (both round to the same float except when the double results straddle a float rounding
+// boundary, ~2^-29 per call) and glibc's expf algorithm for the attenuation factor.
 #pragma once
 #include "common.cuh"
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) image_to_lab_kernel(const float *__restri
     const float Bv = 200 * (fY - fZ);
     const float t0 = (Lv / 100) * (Lv / 100);
     const float t1 = (float)(t0 - 0.6);
-    const float corr = (float)exp((double)(-1.5f * (t1 * t1)));
+    const float corr = expf_glibc_nonpositive(-1.5f * (t1 * t1));  // the reference's exp(float) is expf
     L[p] = Lv;
     A[p] = Av * corr;
     Bp[p] = Bv * corr;

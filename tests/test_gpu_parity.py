@@ -28,7 +28,7 @@ def test_golden(fb, po, case, run):
     u, chi, its, errs = fb.global_solve(method, g["I0n"], g["I1n"], g["u0"], Im1=g["Im1n"], lab=g["lab"], chi=chi0,
                                         warps=warps, glb_iters=iters)
     key = run_key(*run)
-    assert_flow(u, g["u_" + key], exact=method in (0, 4, 8))
+    assert_flow(u, g["u_" + key], exact=True)  # every energy model is bit-identical to the reference
     _, ochi, oits, oerrs = po.o_global_solve(method, g["I0n"], g["I1n"], g["Im1n"], g["lab"], g["u0"], chi0,
                                              warps=warps, glb_iters=iters)
     assert its == oits
@@ -254,12 +254,19 @@ def test_fullsize_reference_pair_other_models(fb, po, method):
     epe = float(np.sqrt(((u - gt) ** 2).sum(0)).mean())
     assert round(epe, 3) == round(float(g["epe_out"]), 3)
     if method == 7:
+        # raw frames: the Lab image comes from the device's double pow, which can differ from glibc's in the
+        # last float bit of a few pixels -> tolerance here; with the reference's own Lab (host preprocessing,
+        # what `global_faldoi -host_preproc 1` does) the flow is bit-identical to the reference executable's
         d = np.abs(u[:, ::8, ::8] - g["u_sub"])
         assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, (d.mean(), d.max())
         full = os.path.join(D, "var_m7.flo")
         if os.path.exists(full):
-            d = np.abs(u - po.read_flo(full))
+            ref = po.read_flo(full)
+            d = np.abs(u - ref)
             assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, (d.mean(), d.max())
+            I0, I1, Im1 = po.o_preprocess(fr[1], fr[2], fr[0])[:3]
+            uh, _, its_h, _ = fb.global_solve(method, I0, I1, u0, Im1=Im1, lab=po.o_image_to_lab(fr[1]), warps=5, glb_iters=400)
+            assert its_h == list(g["iters"]) and np.array_equal(uh, ref)
     else:
         assert np.array_equal(u[:, ::8, ::8], g["u_sub"])
         full = os.path.join(D, "var_m%d.flo" % method)
@@ -267,3 +274,17 @@ def test_fullsize_reference_pair_other_models(fb, po, method):
             assert np.array_equal(u, po.read_flo(full))
     if method == 8:
         assert np.array_equal(chi[::4, ::4].astype(np.uint8), g["chi_sub"]) and int(chi.sum()) == int(g["chi_count"])
+
+
+@pytest.mark.parametrize("method", [2, 6])
+def test_nltv_fast_mode_within_tolerance(fb, po, method, monkeypatch):
+    """FALDOI_NLTV_FAST=1: approximate divisions and paired slot order, the opt-in throughput mode of the NLTV
+    models -- held to the north star's tolerance on the goldens (the default mode is bit-exact, test_golden)."""
+    monkeypatch.setenv("FALDOI_NLTV_FAST", "1")
+    for case in ("crop_a", "crop_b"):
+        g = load_case(case)
+        run = [r for r in CASE_RUNS[case] if r[0] == method][0]
+        u, _, its, _ = fb.global_solve(method, g["I0n"], g["I1n"], g["u0"], Im1=g["Im1n"], lab=g["lab"], warps=run[1], glb_iters=run[2])
+        ref = g["u_" + run_key(*run)]
+        assert not np.array_equal(u, ref), "fast mode did not take effect"
+        assert_flow(u, ref, exact=False)

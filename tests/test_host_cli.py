@@ -139,8 +139,13 @@ def test_cli_end_to_end(H, tmp_path, po, method, warps, iters):
     if method in (0, 4, 8):
         assert np.array_equal(u, g["u_" + key])
     else:
+        # device preprocessing: Lab through the device's double pow (last-bit differences possible)
         d = np.abs(u - g["u_" + key])
         assert d.mean() <= 1e-3 and d.max() <= 1e-2
+        # the reference's own preprocessing on the host: bit-identical flow
+        r2 = subprocess.run(cmd + ["-host_preproc", "1"], capture_output=True, text=True)
+        assert r2.returncode == 0, r2.stderr
+        assert np.array_equal(po.read_flo(out), g["u_" + key])
     log = r.stderr if method in (0, 4) else r.stdout
     assert len(re.findall(r"Warping: \d+, ?Iter: \d+ Error: ", log)) == warps
     if method == 0:
