@@ -176,6 +176,8 @@ def main():
                        % (w, h, B, method, "tvl2OF" if method < 2 else "m%d" % method, a.warps, a.glb_iters if method == 8 else 400),
            "pairs_per_gpu": B, "width": w, "height": h, "method": method, "warps": a.warps,
            "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (B * 24 * npix * 4 / 1e9)}
+    if method in (2, 3, 6, 7):  # NLTV arithmetic: the reference's (bit-identical flows) unless FALDOI_NLTV_FAST=1
+        cfg["nltv_arithmetic"] = "fast (approximate divisions, paired slots)" if os.environ.get("FALDOI_NLTV_FAST", "0") not in ("", "0") else "exact"
     base = {"metric": "global_faldoi Mpix*iter/s", "unit": "Mpix*iter/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg}
