@@ -4,7 +4,7 @@
 // The per-pixel kernel issues ~190 scattered plane loads per pixel and iteration and spends its time
 // on the scoreboard (ncu: 10 of 15.7 cycles per issued instruction are long-scoreboard stalls, 3000
 // instructions per pixel, a third of them address arithmetic).  Here one CTA owns a 128 x 8 pixel tile
-// of one pair (warp = row, lane = 4-pixel quad) and walks the 24 neighbour slots through a 4-stage
+// of one pair (warp = row, lane = 4-pixel quad) and walks the 24 neighbour slots through a small
 // ring of shared-memory buffers filled by TMA box loads:
 //   per slot s, offset (k,l):   wgt[s], P[s], Q[s]         128 x 8 box at (x0,   y0)    -- own
 //                               P[23-s], Q[23-s]           136 x 8 box at (x0-4, y0+k)  -- the neighbour's
@@ -14,7 +14,7 @@
 //                                                          16-byte boundary of global memory: an odd
 //                                                          x origin raises "illegal instruction")
 //   once per tile:              ubar1, ubar2, 1/wt         (128+8) x (8+4) apron boxes
-// Loads of the next three slots are in flight while slot s is computed; out-of-frame parts of a box are
+// Loads of the following slots are in flight while slot s is computed; out-of-frame parts of a box are
 // zero-filled by the TMA unit; slots whose neighbour is outside the frame carry a negative weight and
 // are clamped to zero weight, which is the reference's neighbour-in-image test.
 // New duals go straight to HBM as float4.  Algorithmic traffic is unchanged (532 B / pixel / iteration);
@@ -25,8 +25,13 @@
 
 namespace faldoi {
 
+// Stages of the ring x resident CTAs per SM (register budget).  Measured, 4 pairs, exact / fast mode:
+// 2x3 (62 KB, 80 registers) 5.03 / 10.6 Gpix*iter/s, 4x2 (102 KB, 107 registers) 4.76 / 10.7, 3x2 4.80, 2x2 4.84.
 #ifndef FALDOI_NLT_STAGES
-#define FALDOI_NLT_STAGES 4
+#define FALDOI_NLT_STAGES 2
+#endif
+#ifndef FALDOI_NLT_CTAS
+#define FALDOI_NLT_CTAS 3
 #endif
 enum {
     NLT_W = 128,
@@ -103,7 +108,7 @@ __device__ __forceinline__ void nl_shifted4(const float *row, int l, float (&out
 }
 
 template <int DATA, bool EXACT>
-__global__ void __launch_bounds__(NLT_THREADS, 2) nltv_tile_kernel(const __grid_constant__ NlTileMaps maps, NlArgs a, int it, int base_parity) {
+__global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel(const __grid_constant__ NlTileMaps maps, NlArgs a, int it, int base_parity) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     NlTileSmem &S = *reinterpret_cast<NlTileSmem *>(smem_raw);
     const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
