@@ -288,3 +288,29 @@ def test_nltv_fast_mode_within_tolerance(fb, po, method, monkeypatch):
         ref = g["u_" + run_key(*run)]
         assert not np.array_equal(u, ref), "fast mode did not take effect"
         assert_flow(u, ref, exact=False)
+
+
+@pytest.mark.parametrize("method,warps,iters", [(4, 1, 400), (2, 1, 400), (6, 1, 400), (8, 1, 6)])
+def test_batch_equals_oracle_other_models(fb, po, method, warps, iters):
+    """The batched handle with the other energy models: every slot of a batch of different pairs equals the
+    oracle's solve of that pair bit for bit (tile staging, TMA maps and the CSAD / NLTV tables are all indexed
+    by slot)."""
+    w, h, B = 70, 37, 3  # ragged: not a multiple of the quad or of any tile
+    pairs = [synthetic_pair(w, h, seed=300 + k, max_flow=1.0 + k) for k in range(B)]
+    labs = [po.o_image_to_lab(p[4]) for p in pairs]
+    chis = [(np.random.default_rng(k).random((h, w)) > 0.8).astype(np.float32) for k in range(B)]
+    s = fb.Solver(w, h, method, B)
+    for k, (I0, I1, Im1, u0, _) in enumerate(pairs):
+        s.upload(k, I0, I1, u0, Im1=Im1 if method == 8 else None, lab=labs[k] if method in (2, 6) else None,
+                 chi=chis[k] if method == 8 else None)
+    p = fb.default_params(method, glb_iters=iters, warps=warps)
+    s.run(p)
+    for k, (I0, I1, Im1, u0, _) in enumerate(pairs):
+        u, chi, log = s.download(k)
+        ou, ochi, oits, _ = po.o_global_solve(method, I0, I1, Im1, labs[k], u0, chis[k] if method == 8 else None, warps=warps,
+                                              glb_iters=iters)
+        assert list(log.iters[:warps]) == oits
+        assert np.array_equal(u, ou), "slot %d: max |du| = %g" % (k, np.abs(u - ou).max())
+        if method == 8:
+            assert np.array_equal(chi, ochi)
+    s.close()
