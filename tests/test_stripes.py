@@ -63,10 +63,12 @@ def test_sharding_logic_gloo_world2(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sync", ["events", "memops"])
 @pytest.mark.parametrize("w,h,n", [(160, 70, 2), (160, 70, 3), (96, 33, 4), (300, 131, 5)])
-def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n):
-    """All stripes on device 0: exercises halo rows, peer stores, event ordering and the global
-    error gather without needing several GPUs."""
+def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n, sync, monkeypatch):
+    """All stripes on device 0: exercises halo rows, peer stores, the cross-stripe ordering (events + host
+    barrier, or stream memory operations) and the global error gather without needing several GPUs."""
+    monkeypatch.setenv("FALDOI_STRIPES_SYNC", sync)
     I0, I1, _, u0, _ = synthetic_pair(w, h, seed=w * 7 + h + n)
     p = fb.default_params(0, warps=3)
     whole, _, its, errs = fb.global_solve(0, I0, I1, u0, params=p)
@@ -82,8 +84,10 @@ def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n):
 
 
 @pytest.mark.gpu
-def test_striped_across_gpus(fb):
+@pytest.mark.parametrize("sync", ["events", "memops"])
+def test_striped_across_gpus(fb, sync, monkeypatch):
     """With >= 2 GPUs: one stripe per GPU, NVLink peer stores."""
+    monkeypatch.setenv("FALDOI_STRIPES_SYNC", sync)
     n = min(fb.device_count(), 8)
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
