@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) occ_xi_sweep_kernel(OccArgs a, int it, in
             gy = vi_d - vi_c;
         }
         const float e1 = gp * gx, e2 = gp * gy;
-        const float nrm = sqrtf(e1 * e1 + e2 * e2);
+        const float nrm = sqrt_or_zero(e1 * e1 + e2 * e2);
         xout[(size_t)(2 * c) * ks + p] = (xa[p] + tt * e1) / (1 + tt * nrm);
         xout[(size_t)(2 * c + 1) * ks + p] = (xb[p] + tt * e2) / (1 + tt * nrm);
     }
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) occ_xi_multi_kernel(OccArgs a, int it, in
                 const float gxv = (gx < w - 1) ? svi[c][l + 1] - vi_c : 0.f;
                 const float gyv = (gy < h - 1) ? svi[c][l + SW] - vi_c : 0.f;
                 const float e1 = gp * gxv, e2 = gp * gyv;
-                const float nrm = sqrtf(e1 * e1 + e2 * e2);
+                const float nrm = sqrt_or_zero(e1 * e1 + e2 * e2);
                 float q1 = sx[2 * c][l] + tt * e1, q2 = sx[2 * c + 1][l] + tt * e2;
                 div2_shared(q1, q2, 1 + tt * nrm);
                 sx[2 * c][l] = q1;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_xi_rows_kernel(OccA
                 const float gxv = (gx < w - 1) ? (k < 3 ? vi1[k + 1] : rv1) - vi1[k] : 0.f;
                 const float gyv = (gy < h - 1) ? dn1[k] - vi1[k] : 0.f;
                 const float e1 = g[k] * gxv, e2 = g[k] * gyv;
-                const float nrm = sqrtf(e1 * e1 + e2 * e2);
+                const float nrm = sqrt_or_zero(e1 * e1 + e2 * e2);
                 float q1 = x11[k] + tt * e1, q2 = x12[k] + tt * e2;
                 div2_shared(q1, q2, 1 + tt * nrm);
                 x11[k] = q1;
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_xi_rows_kernel(OccA
                 const float gxv = (gx < w - 1) ? (k < 3 ? vi2[k + 1] : rv2) - vi2[k] : 0.f;
                 const float gyv = (gy < h - 1) ? dn2[k] - vi2[k] : 0.f;
                 const float e1 = g[k] * gxv, e2 = g[k] * gyv;
-                const float nrm = sqrtf(e1 * e1 + e2 * e2);
+                const float nrm = sqrt_or_zero(e1 * e1 + e2 * e2);
                 float q1 = x21[k] + tt * e1, q2 = x22[k] + tt * e2;
                 div2_shared(q1, q2, 1 + tt * nrm);
                 x21[k] = q1;
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(32 * (OR_TH + 2 * NS)) occ_chi_rows_kernel(Occ
             const float chiy = (gy < h - 1) ? dn[k] - c[k] : 0.f;
             const float n1 = e1[k] + mte * g[k] * chix;
             const float n2 = e2[k] + mte * g[k] * chiy;
-            const float ne = sqrtf(n1 * n1 + n2 * n2);
+            const float ne = sqrt_or_zero(n1 * n1 + n2 * n2);
             if (ne <= 1) {
                 e1[k] = n1;
                 e2[k] = n2;
