@@ -249,13 +249,25 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
                     // (sc + tau*g)/(1 + tau*sqrt(g*g)); sqrt(g*g) == |g| whenever g*g is a normal float, and
                     // below that 1 + tau*(either) rounds to 1.  A slot without neighbour divides by 1, not by
                     // the zero fill.
-                    const float wq = wm > 0.f ? nrw[i] : 1.f;
-                    const float g1 = t1 / rwp[i], g2 = t2 / rwp[i];
-                    pn[i] = (po[i] + tau * g1) / (1 + tau * fabsf(g1));
-                    qn[i] = (qo[i] + tau * g2) / (1 + tau * fabsf(g2));
-                    const float h1 = -t1 / wq, h2 = -t2 / wq;
-                    Pr = (pr[i] + tau * h1) / (1 + tau * fabsf(h1));
-                    Qr = (qr[i] + tau * h2) / (1 + tau * fabsf(h2));
+                    if (t1 == 0.f && t2 == 0.f) {
+                        // Slots without a neighbour (weight clamped to 0), the pitch padding and flat regions:
+                        // g = 0/wt = 0 with the sign of t, and the update divides by exactly 1.  Same bits as the
+                        // general branch, but these lanes stay out of it: IEEE division sends zero numerators to
+                        // its out-of-line slow path, and one such lane drags the whole warp along (14 % of the
+                        // kernel's instructions before this test).
+                        pn[i] = po[i] + tau * t1;
+                        qn[i] = qo[i] + tau * t2;
+                        Pr = pr[i] + tau * -t1;
+                        Qr = qr[i] + tau * -t2;
+                    } else {
+                        const float wq = wm > 0.f ? nrw[i] : 1.f;
+                        const float g1 = t1 / rwp[i], g2 = t2 / rwp[i];
+                        pn[i] = (po[i] + tau * g1) / (1 + tau * fabsf(g1));
+                        qn[i] = (qo[i] + tau * g2) / (1 + tau * fabsf(g2));
+                        const float h1 = -t1 / wq, h2 = -t2 / wq;
+                        Pr = (pr[i] + tau * h1) / (1 + tau * fabsf(h1));
+                        Qr = (qr[i] + tau * h2) / (1 + tau * fabsf(h2));
+                    }
                 } else {
                     const float rwq = nrw[i];
                     // own dual, slot s
