@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256, 4) nltv_iter_kernel(NlArgs a, int it, int
                 const float s = (ix * u1 + iy * u2) / sc;
                 const int np = csad_count(x, y, w, h);
                 const float med = csad_select(a.blk, a.sep, a.g, b, y, x, np, s, l_t, sc);
-                v1 = u1 - ix * med / sc;
-                v2 = u2 - iy * med / sc;
+                v1 = csad_apply(u1, ix, med, sc);
+                v2 = csad_apply(u2, iy, med, sc);
             }
         }
 

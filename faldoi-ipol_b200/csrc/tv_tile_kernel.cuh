@@ -218,11 +218,15 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
                 if (DATA == DATA_TVL1) {
                     if (nr1[k] > 1.f) div4_shared(x11[k], x12[k], x21[k], x22[k], nr1[k]);
                 } else {
-                    const float d1 = fmaxf(1.f, nr1[k]), d2 = fmaxf(1.f, nr2[k]);
-                    x11[k] /= d1;
-                    x12[k] /= d1;
-                    x21[k] /= d2;
-                    x22[k] /= d2;
+                    // divide by max(1, |xi_old|): x / 1 == x, so only saturated rows divide
+                    if (nr1[k] > 1.f) {
+                        x11[k] /= nr1[k];
+                        x12[k] /= nr1[k];
+                    }
+                    if (nr2[k] > 1.f) {
+                        x21[k] /= nr2[k];
+                        x22[k] /= nr2[k];
+                    }
                 }
             }
         }
@@ -323,8 +327,8 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
                 v1 = u1[k];
                 v2 = u2[k];
                 if (gx < w) {
-                    v1 = u1[k] - ix[k] * med[k] / cc[k];
-                    v2 = u2[k] - iy[k] * med[k] / cc[k];
+                    v1 = csad_apply(u1[k], ix[k], med[k], cc[k]);
+                    v2 = csad_apply(u2[k], iy[k], med[k], cc[k]);
                 }
             }
             o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
