@@ -254,16 +254,15 @@ def test_fullsize_reference_pair_other_models(fb, po, method):
     epe = float(np.sqrt(((u - gt) ** 2).sum(0)).mean())
     assert round(epe, 3) == round(float(g["epe_out"]), 3)
     if method == 7:
-        # raw frames: the Lab image comes from the device's double pow, which can differ from glibc's in the
-        # last float bit of a few pixels -> tolerance here; with the reference's own Lab (host preprocessing,
-        # what `global_faldoi -host_preproc 1` does) the flow is bit-identical to the reference executable's
-        d = np.abs(u[:, ::8, ::8] - g["u_sub"])
-        assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, (d.mean(), d.max())
+        # raw frames: gray / normalise / Gaussian / Lab all on the device (the Lab attenuation uses glibc's expf
+        # algorithm; its cube roots use the device's double pow, which rounds to the same floats as glibc's on
+        # this frame) -> the flow is bit-identical to the reference executable's, as with the reference's own
+        # host-side preprocessing
+        assert np.array_equal(u[:, ::8, ::8], g["u_sub"])
         full = os.path.join(D, "var_m7.flo")
         if os.path.exists(full):
             ref = po.read_flo(full)
-            d = np.abs(u - ref)
-            assert d.mean() <= MEAN_TOL and d.max() <= MAX_TOL, (d.mean(), d.max())
+            assert np.array_equal(u, ref), "max |du| = %g" % np.abs(u - ref).max()
             I0, I1, Im1 = po.o_preprocess(fr[1], fr[2], fr[0])[:3]
             uh, _, its_h, _ = fb.global_solve(method, I0, I1, u0, Im1=Im1, lab=po.o_image_to_lab(fr[1]), warps=5, glb_iters=400)
             assert its_h == list(g["iters"]) and np.array_equal(uh, ref)
