@@ -193,6 +193,30 @@ def test_cli_fullsize_real_pair_is_bit_identical_to_reference(H, tmp_path, po):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method", [4, 7, 8])
+def test_cli_fullsize_other_models_byte_identical(H, tmp_path, po, method):
+    """Same claim for TV-CSAD, NLTV-CSAD(-W) and TVL2-OCC: the .flo (and the occlusion PNG's pixels) our
+    executable writes for the Sintel pair equal what the reference executable wrote (oracle/run_full_refs.sh)."""
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "clean_easy")
+    ref = os.path.join(D, "var_m%d.flo" % method)
+    flo = os.path.join(D, "rg_m8.flo" if method == 8 else "rg.flo")
+    if not os.path.exists(ref) or not os.path.exists(flo):
+        pytest.skip("full-size reference outputs not present")
+    names = [os.path.join(D, "frame_%04d.png" % k) for k in (2, 3, 1, 4)]
+    (tmp_path / "ims.txt").write_text("\n".join(names) + "\n")
+    out = str(tmp_path / "out.flo")
+    cmd = [BIN, str(tmp_path / "ims.txt"), flo, out]
+    if method == 8:
+        cmd += [os.path.join(D, "rg_occ.png"), str(tmp_path / "occ.png")]
+    r = subprocess.run(cmd + ["-m", str(method), "-w", "5", "-glb_iters", "400"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(ref, "rb").read()
+    if method == 8:
+        from PIL import Image
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "occ.png")), np.asarray(Image.open(os.path.join(D, "var_m8_occ.png"))))
+
+
+@pytest.mark.gpu
 def test_cli_sequence_mode(H, tmp_path, po):
     """-seq jobs.txt: several pairs in one process (one CUDA start-up), each result as in a single call."""
     g = load_case("crop_b")
