@@ -101,6 +101,34 @@ def make_fullsize_others():
         np.savez_compressed(os.path.join(OUT, "fullsize_clean_easy_m%d.npz" % m), **out)
 
 
+def make_fullsize_seq(seq="final/hard"):
+    """A second full-size anchor (oracle/run_full_refs_seq.sh): methods 0 and 4 on another example sequence."""
+    import re
+    tag = seq.replace("/", "_")
+    D = os.path.join(ROOT, "oracle", "_ref", "data", tag)
+    gt = po.read_flo(os.path.join(REF, "example_data", seq, "gt", "frame_0002.flo"))
+    epe = lambda a: float(np.sqrt(((a - gt) ** 2).sum(0)).mean())
+    rg = po.read_flo(os.path.join(D, "rg.flo"))
+    # Method 4 is anchored on a SINGLE-THREADED reference run (OMP_NUM_THREADS=1, -w 1): tvcsad_getP accumulates
+    # its error with an unsynchronised `err_D +=` inside `#pragma omp parallel for` (src/global_faldoi.cpp:1398-1419),
+    # so with several threads the reference sees only a fraction of the sum and, on this pair, leaves the loop
+    # after 34/7/16/2/18 iterations -- an artefact of the data race, recorded as `racy_iters` for reference only.
+    for m, f, logf, tag2 in ((0, "var_m0.flo", "log_m0.txt", "m0"), (4, "var_m4_w1_t1.flo", "log_m4_w1_t1.txt", "m4")):
+        f = os.path.join(D, f)
+        if not os.path.exists(f):
+            print("skip", seq, "method", m, "(run oracle/run_full_refs_seq.sh first)")
+            continue
+        var = po.read_flo(f)
+        log = open(os.path.join(D, logf)).read()
+        iters = [int(x) for x in re.findall(r"Warping: \d+, ?Iter: (\d+)", log)]
+        extra = {}
+        if m == 4 and os.path.exists(os.path.join(D, "log_m4.txt")):
+            extra["racy_iters"] = np.array([int(x) for x in re.findall(r"Warping: \d+, ?Iter: (\d+)", open(os.path.join(D, "log_m4.txt")).read())])
+        print("full-size %s m%d iters %s EPE init %.4f -> %.4f" % (seq, m, iters, epe(rg), epe(var)), extra)
+        np.savez_compressed(os.path.join(OUT, "fullsize_%s_%s.npz" % (tag, tag2)), iters=np.array(iters), epe_init=epe(rg),
+                            epe_out=epe(var), u_sub=var[:, ::8, ::8].copy(), **extra)
+
+
 if __name__ == "__main__":
     assert po.have_ref(), "build the reference first: make -C oracle ref"
     # 96x64 crop, every energy model (the reference always runs 400 iterations for methods 0-7)
@@ -109,3 +137,4 @@ if __name__ == "__main__":
     make_case("crop_b", "clean/easy", 3, 5, 61, 45, [(0, 3, 400), (4, 1, 400), (2, 1, 400), (6, 1, 400), (8, 1, 12)])
     make_fullsize_anchor()
     make_fullsize_others()
+    make_fullsize_seq("final/hard")

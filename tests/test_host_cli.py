@@ -217,6 +217,35 @@ def test_cli_fullsize_other_models_byte_identical(H, tmp_path, po, method):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method", [0, 4])
+def test_cli_fullsize_second_sequence_byte_identical(H, tmp_path, po, method):
+    """A second Sintel pair (final/hard: motion blur, large displacements; oracle/run_full_refs_seq.sh): the CLI's
+    .flo equals the reference executable's byte for byte, iteration counts and EPE as recorded in the golden.
+    TV-CSAD is compared with a single-threaded reference run of one warp: with several OpenMP threads the
+    reference's unsynchronised error sum (tvcsad_getP) loses most of its terms and ends the loop early."""
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "final_hard")
+    ref = os.path.join(D, "var_m0.flo" if method == 0 else "var_m4_w1_t1.flo")
+    gfile = os.path.join(ROOT, "tests", "golden", "fullsize_final_hard_m%d.npz" % method)
+    if not os.path.exists(ref) or not os.path.exists(gfile):
+        pytest.skip("final/hard reference outputs not present")
+    g = dict(np.load(gfile))
+    warps = 5 if method == 0 else 1
+    names = [os.path.join(D, "frame_%04d.png" % k) for k in (2, 3, 1, 4)]
+    (tmp_path / "ims.txt").write_text("\n".join(names) + "\n")
+    out = str(tmp_path / "out.flo")
+    r = subprocess.run([BIN, str(tmp_path / "ims.txt"), os.path.join(D, "rg.flo"), out, "-m", str(method), "-w", str(warps), "-verbose", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    iters = [int(x) for x in re.findall(r"Warping: \d+,Iter: (\d+)", r.stderr)]
+    assert iters == list(g["iters"])
+    assert open(out, "rb").read() == open(ref, "rb").read()
+    u = po.read_flo(out)
+    assert np.array_equal(u[:, ::8, ::8], g["u_sub"])
+    gt = po.read_flo(os.path.join(D, "gt_frame_0002.flo"))
+    assert round(float(np.sqrt(((u - gt) ** 2).sum(0)).mean()), 3) == round(float(g["epe_out"]), 3)
+
+
+@pytest.mark.gpu
 def test_cli_sequence_mode(H, tmp_path, po):
     """-seq jobs.txt: several pairs in one process (one CUDA start-up), each result as in a single call."""
     g = load_case("crop_b")
