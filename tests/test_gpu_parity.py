@@ -313,3 +313,22 @@ def test_batch_equals_oracle_other_models(fb, po, method, warps, iters):
         if method == 8:
             assert np.array_equal(chi, ochi)
     s.close()
+
+
+@pytest.mark.parametrize("tol", [0.05, 0.15, 0.3, 1.0])
+def test_tvcsad_exit_test(fb, po, tol):
+    """TV-CSAD leaves a warp when the mean squared update drops to tol^2 (src/global_faldoi.cpp:1543; the sum over
+    ALL pixels, which is what the reference computes with one thread -- DESIGN.md on the racy err_D).  Larger
+    tolerances make the exit happen early and at different iterations per warp."""
+    I0, I1, _, u0, _ = synthetic_pair(140, 50, seed=21, max_flow=1.5)
+    p = fb.default_params(4, warps=3)
+    p.tol = tol
+    u, _, its, errs = fb.global_solve(4, I0, I1, u0, params=p)
+    op = po.default_params()
+    op.tol = tol
+    ou, _, oits, oerrs = po.o_global_solve(4, I0, I1, None, None, u0, params=op, warps=3)
+    assert its == oits, (its, oits)
+    assert np.array_equal(u, ou)
+    assert np.allclose(errs, oerrs, rtol=1e-4)
+    if tol >= 0.3:
+        assert min(its) < 400, "the exit test was never met: %s" % its
