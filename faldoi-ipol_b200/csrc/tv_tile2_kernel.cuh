@@ -24,12 +24,14 @@ namespace faldoi {
 
 // Geometry: the staged region is 128 columns (32 float4 quads, x0-4 .. x0+123) so that ONE WARP
 // owns one staged row and a lane owns one quad -- no index arithmetic, row tests are warp-uniform,
-// and every phase is a single balanced round: 11 / 10 / 9 / 8 busy warps of the CTA's 11.  The tile
-// written back is the inner 120 x 8 pixels (quads 1..30).
-// FALDOI_T2_H / FALDOI_T2_CTAS: tile rows and resident CTAs per SM (8 rows, 11 warps, 60 KB -> 3 CTAs;
-// taller tiles recompute relatively less apron but hold fewer, larger CTAs -- profiles/README.md)
+// and every phase is a single balanced round: H+3 / H+2 / H+1 / H busy warps of the CTA's H+3.  The tile
+// written back is the inner 120 x H pixels (quads 1..30).
+// FALDOI_T2_H / FALDOI_T2_CTAS: tile rows and resident CTAs per SM.  H = 9: 12 warps, 66 KB, 56 registers ->
+// 3 CTAs per SM; a 1024x436 pair is 9 x 49 = 441 CTAs, one wave of the 444 resident slots (H = 8 needs 495:
+// a second, nearly empty wave, which is what single-pair latency paid for).  Measured 1 / 2 / 64 pairs:
+// H=8 31.3 / 46.2 / 67.7, H=9 39.0 / 48.3 / 70.3, H=10 (48 registers, spills) 33.1 / 40.4 / 61.9 Gpix*iter/s.
 #ifndef FALDOI_T2_H
-#define FALDOI_T2_H 8
+#define FALDOI_T2_H 9
 #endif
 #ifndef FALDOI_T2_CTAS
 #define FALDOI_T2_CTAS 3
