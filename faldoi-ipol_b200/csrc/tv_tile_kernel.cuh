@@ -350,25 +350,6 @@ __global__ void __launch_bounds__(TT_THREADS, DATA == DATA_CSAD ? FALDOI_TT_CTAS
         st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
         st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
         st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
-        // stripe boundaries: the same values go straight into the neighbour GPU's halo row (peer stores)
-        if (a.peer_up && y == a.g.own_lo) {
-            float *po = a.peer_up + (size_t)(par ^ 1) * a.peer_up_set + (size_t)a.peer_up_row * pitch + gx0;
-            st4(po + ST_U1 * a.peer_up_plane, make_float4(o1[0], o1[1], o1[2], o1[3]));
-            st4(po + ST_U2 * a.peer_up_plane, make_float4(o2[0], o2[1], o2[2], o2[3]));
-            st4(po + ST_UB1 * a.peer_up_plane, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
-            st4(po + ST_UB2 * a.peer_up_plane, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
-        }
-        if (a.peer_dn && y == a.g.own_hi - 1) {
-            float *po = a.peer_dn + (size_t)(par ^ 1) * a.peer_dn_set + (size_t)a.peer_dn_row * pitch + gx0;
-            st4(po + ST_U1 * a.peer_dn_plane, make_float4(o1[0], o1[1], o1[2], o1[3]));
-            st4(po + ST_U2 * a.peer_dn_plane, make_float4(o2[0], o2[1], o2[2], o2[3]));
-            st4(po + ST_UB1 * a.peer_dn_plane, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
-            st4(po + ST_UB2 * a.peer_dn_plane, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
-            st4(po + ST_XI11 * a.peer_dn_plane, M11);
-            st4(po + ST_XI12 * a.peer_dn_plane, M12);
-            st4(po + ST_XI21 * a.peer_dn_plane, M21);
-            st4(po + ST_XI22 * a.peer_dn_plane, M22);
-        }
     }
 
     // ---- convergence measure ----
