@@ -38,3 +38,22 @@ def test_fullsize_anchor_is_recorded():
     # anchors measured on the reference: SURVEY.md 8(c)
     assert list(g["iters"]) == [400, 152, 100, 82, 136]
     assert round(float(g["epe_init"]), 4) == 0.3298 and round(float(g["epe_out"]), 4) == 0.2232
+
+
+def test_oracle_fullsize_second_sequence(po):
+    """The C restatement against the reference EXECUTABLE's output on a whole Sintel pair (final/hard, TVL2,
+    5 warps x 400 iterations): same flow in every bit.  Needs oracle/_ref/data/final_hard
+    (oracle/run_full_refs_seq.sh); about 10 s on 8 cores."""
+    import os
+    from conftest import ROOT
+    D = os.path.join(ROOT, "oracle", "_ref", "data", "final_hard")
+    ref = os.path.join(D, "var_m0.flo")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/data/final_hard not present")
+    g = load_case("fullsize_final_hard_m0")
+    fr = [po.read_image_planar(os.path.join(D, "frame_%04d.png" % k)) for k in (1, 2, 3)]
+    I0, I1, _ = po.o_preprocess(fr[1], fr[2], fr[0])[:3]
+    u, _, its, _ = po.o_global_solve(0, I0, I1, None, None, po.read_flo(os.path.join(D, "rg.flo")), warps=5)
+    assert its == list(g["iters"])
+    assert np.array_equal(u, po.read_flo(ref))
+    assert np.array_equal(u[:, ::8, ::8], g["u_sub"])
