@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -14,19 +15,33 @@ namespace faldoi_host {
 namespace {
 
 std::vector<uint8_t> slurp(const std::string &path) {
-    std::ifstream f(path, std::ios::binary);
+    FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("cannot open '" + path + "'");
-    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<uint8_t> buf;
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long n = std::ftell(f);
+        std::rewind(f);
+        if (n > 0) {
+            buf.resize((size_t)n);
+            buf.resize(std::fread(buf.data(), 1, (size_t)n, f));
+        }
+    } else {  // not seekable: read in pieces
+        uint8_t tmp[65536];
+        size_t got;
+        while ((got = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    }
+    std::fclose(f);
     return buf;
 }
 
 uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
 
 // ---------------------------------------------------------------- PNG
-int paeth(int a, int b, int c) {
-    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-    if (pa <= pb && pa <= pc) return a;
-    return pb <= pc ? b : c;
+inline int paeth(int a, int b, int c) {
+    // p = a + b - c; |p - a| = |b - c|, |p - b| = |a - c|, |p - c| = |a + b - 2c|; selects instead of branches
+    const int pa = std::abs(b - c), pb = std::abs(a - c), pc = std::abs(a + b - 2 * c);
+    const int bc = pb <= pc ? b : c;
+    return (pa <= pb && pa <= pc) ? a : bc;
 }
 
 Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
@@ -77,25 +92,34 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
     uLongf outlen = raw.size();
     if (uncompress(raw.data(), &outlen, idat.data(), idat.size()) != Z_OK || outlen != raw.size())
         throw bad("zlib inflate failed");
-    // undo the scanline filters in place
+    // undo the scanline filters (one specialised loop per filter type; the first `bpp` bytes of a row have
+    // no left neighbour)
     std::vector<uint8_t> pix(stride * h);
+    const std::vector<uint8_t> zero_row(stride, 0);
     for (uint32_t y = 0; y < h; y++) {
         const uint8_t ft = raw[y * (stride + 1)];
         const uint8_t *in = &raw[y * (stride + 1) + 1];
         uint8_t *cur = &pix[y * stride];
-        const uint8_t *up = y ? &pix[(y - 1) * stride] : nullptr;
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
-            int v = in[i];
-            switch (ft) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) / 2; break;
-                case 4: v += paeth(a, b, c); break;
-                default: throw bad("bad filter type");
-            }
-            cur[i] = (uint8_t)v;
+        const uint8_t *up = y ? &pix[(y - 1) * stride] : zero_row.data();
+        const size_t head = std::min(bpp, stride);
+        switch (ft) {
+            case 0: memcpy(cur, in, stride); break;
+            case 1:
+                for (size_t i = 0; i < head; i++) cur[i] = in[i];
+                for (size_t i = head; i < stride; i++) cur[i] = (uint8_t)(in[i] + cur[i - bpp]);
+                break;
+            case 2:
+                for (size_t i = 0; i < stride; i++) cur[i] = (uint8_t)(in[i] + up[i]);
+                break;
+            case 3:
+                for (size_t i = 0; i < head; i++) cur[i] = (uint8_t)(in[i] + up[i] / 2);
+                for (size_t i = head; i < stride; i++) cur[i] = (uint8_t)(in[i] + (cur[i - bpp] + up[i]) / 2);
+                break;
+            case 4:
+                for (size_t i = 0; i < head; i++) cur[i] = (uint8_t)(in[i] + paeth(0, up[i], 0));
+                for (size_t i = head; i < stride; i++) cur[i] = (uint8_t)(in[i] + paeth(cur[i - bpp], up[i], up[i - bpp]));
+                break;
+            default: throw bad("bad filter type");
         }
     }
     Image im;
@@ -105,6 +129,17 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
     im.pd = pal ? 3 : channels;
     const size_t n = (size_t)w * h;
     im.data.assign(n * im.pd, 0.f);
+    if (depth == 8 && !pal) {  // the common case (8-bit gray / RGB / RGBA): straight de-interleave
+        for (int c = 0; c < channels; c++) {
+            float *dst = &im.data[c * n];
+            for (uint32_t y = 0; y < h; y++) {
+                const uint8_t *row = &pix[y * stride] + c;
+                float *d = dst + (size_t)y * w;
+                for (uint32_t x = 0; x < w; x++) d[x] = (float)row[(size_t)x * channels];
+            }
+        }
+        return im;
+    }
     for (uint32_t y = 0; y < h; y++) {
         const uint8_t *row = &pix[y * stride];
         for (uint32_t x = 0; x < w; x++)
