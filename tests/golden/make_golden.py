@@ -129,6 +129,24 @@ def make_fullsize_seq(seq="final/hard"):
                             epe_out=epe(var), u_sub=var[:, ::8, ::8].copy(), **extra)
 
 
+def make_fullsize_tvl2(seq):
+    """TVL2 anchors of the remaining example sequences (oracle/run_full_refs_all.sh)."""
+    import re
+    tag = seq.replace("/", "_")
+    D = os.path.join(ROOT, "oracle", "_ref", "data", tag)
+    f = os.path.join(D, "var_m0.flo")
+    if not os.path.exists(f):
+        print("skip", seq, "(run oracle/run_full_refs_all.sh first)")
+        return
+    gt = po.read_flo(os.path.join(REF, "example_data", seq, "gt", "frame_0002.flo"))
+    epe = lambda a: float(np.sqrt(((a - gt) ** 2).sum(0)).mean())
+    var, rg = po.read_flo(f), po.read_flo(os.path.join(D, "rg.flo"))
+    iters = [int(x) for x in re.findall(r"Warping: \d+, ?Iter: (\d+)", open(os.path.join(D, "log_m0.txt")).read())]
+    print("full-size %s m0 iters %s EPE init %.4f -> %.4f" % (seq, iters, epe(rg), epe(var)))
+    np.savez_compressed(os.path.join(OUT, "fullsize_%s_m0.npz" % tag), iters=np.array(iters), epe_init=epe(rg), epe_out=epe(var),
+                        u_sub=var[:, ::8, ::8].copy())
+
+
 if __name__ == "__main__":
     assert po.have_ref(), "build the reference first: make -C oracle ref"
     # 96x64 crop, every energy model (the reference always runs 400 iterations for methods 0-7)
@@ -138,3 +156,5 @@ if __name__ == "__main__":
     make_fullsize_anchor()
     make_fullsize_others()
     make_fullsize_seq("final/hard")
+    for seq in ("clean/medium", "clean/hard", "final/easy", "final/medium"):
+        make_fullsize_tvl2(seq)

@@ -246,6 +246,30 @@ def test_cli_fullsize_second_sequence_byte_identical(H, tmp_path, po, method):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seq", ["clean_medium", "clean_hard", "final_easy", "final_medium"])
+def test_cli_fullsize_tvl2_remaining_sequences(H, tmp_path, po, seq):
+    """TVL2 on the other example sequences of the reference: byte-identical .flo, same
+    per-warp iteration counts, EPE equal to 3 decimals."""
+    D = os.path.join(ROOT, "oracle", "_ref", "data", seq)
+    ref = os.path.join(D, "var_m0.flo")
+    gfile = os.path.join(ROOT, "tests", "golden", "fullsize_%s_m0.npz" % seq)
+    if not os.path.exists(ref) or not os.path.exists(gfile):
+        pytest.skip("%s reference outputs not present" % seq)
+    g = dict(np.load(gfile))
+    names = [os.path.join(D, "frame_%04d.png" % k) for k in (2, 3, 1, 4)]
+    (tmp_path / "ims.txt").write_text("\n".join(names) + "\n")
+    out = str(tmp_path / "out.flo")
+    r = subprocess.run([BIN, str(tmp_path / "ims.txt"), os.path.join(D, "rg.flo"), out, "-m", "0", "-w", "5", "-verbose", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert [int(x) for x in re.findall(r"Warping: \d+,Iter: (\d+)", r.stderr)] == list(g["iters"])
+    assert open(out, "rb").read() == open(ref, "rb").read()
+    gt = po.read_flo(os.path.join(D, "gt_frame_0002.flo"))
+    u = po.read_flo(out)
+    assert round(float(np.sqrt(((u - gt) ** 2).sum(0)).mean()), 3) == round(float(g["epe_out"]), 3)
+
+
+@pytest.mark.gpu
 def test_cli_sequence_mode(H, tmp_path, po):
     """-seq jobs.txt: several pairs in one process (one CUDA start-up), each result as in a single call."""
     g = load_case("crop_b")

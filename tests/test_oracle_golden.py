@@ -40,17 +40,18 @@ def test_fullsize_anchor_is_recorded():
     assert round(float(g["epe_init"]), 4) == 0.3298 and round(float(g["epe_out"]), 4) == 0.2232
 
 
-def test_oracle_fullsize_second_sequence(po):
-    """The C restatement against the reference EXECUTABLE's output on a whole Sintel pair (final/hard, TVL2,
-    5 warps x 400 iterations): same flow in every bit.  Needs oracle/_ref/data/final_hard
-    (oracle/run_full_refs_seq.sh); about 10 s on 8 cores."""
+@pytest.mark.parametrize("seq", ["final_hard", "clean_medium", "clean_hard", "final_easy", "final_medium"])
+def test_oracle_fullsize_other_sequences(po, seq):
+    """The C restatement against the reference EXECUTABLE's output on whole Sintel pairs (TVL2, 5 warps x <= 400
+    iterations): same iteration counts, same flow in every bit.  Needs oracle/_ref/data/<seq>
+    (oracle/run_full_refs_seq.sh, run_full_refs_all.sh); 5-20 s each on 8 cores."""
     import os
     from conftest import ROOT
-    D = os.path.join(ROOT, "oracle", "_ref", "data", "final_hard")
+    D = os.path.join(ROOT, "oracle", "_ref", "data", seq)
     ref = os.path.join(D, "var_m0.flo")
     if not os.path.exists(ref):
-        pytest.skip("oracle/_ref/data/final_hard not present")
-    g = load_case("fullsize_final_hard_m0")
+        pytest.skip("oracle/_ref/data/%s not present" % seq)
+    g = load_case("fullsize_%s_m0" % seq)
     fr = [po.read_image_planar(os.path.join(D, "frame_%04d.png" % k)) for k in (1, 2, 3)]
     I0, I1, _ = po.o_preprocess(fr[1], fr[2], fr[0])[:3]
     u, _, its, _ = po.o_global_solve(0, I0, I1, None, None, po.read_flo(os.path.join(D, "rg.flo")), warps=5)
