@@ -51,7 +51,8 @@ EXPORTS = [
     "faldoi_bicubic_warp", "faldoi_stripe_rows", "faldoi_stripes_create", "faldoi_stripes_destroy",
     "faldoi_stripes_upload", "faldoi_stripes_run", "faldoi_stripes_download", "faldoi_stripes_last_run_ms",
     "faldoi_stripes_last_launches", "faldoi_selftest_division", "faldoi_solver_upload_raw",
-    "faldoi_solver_download_frames", "faldoi_global_solve_raw",
+    "faldoi_solver_download_frames", "faldoi_global_solve_raw", "faldoi_solver_set_nltv_fast",
+    "faldoi_solver_upload_xi", "faldoi_solver_download_xi", "faldoi_pinned_alloc", "faldoi_pinned_free",
 ]
 
 
@@ -104,6 +105,12 @@ def lib():
         L.faldoi_solver_upload_raw.argtypes = [vp, i, vp, vp, vp, i, vp, vp]
         L.faldoi_solver_download_frames.argtypes = [vp, i, vp, vp, vp, vp]
         L.faldoi_global_solve_raw.argtypes = [i, C.POINTER(Params), i, i, i, vp, vp, vp, vp, vp, C.POINTER(Log)]
+        L.faldoi_solver_set_nltv_fast.argtypes = [vp, i]
+        L.faldoi_solver_upload_xi.argtypes = [vp, i, vp, vp, vp, vp]
+        L.faldoi_solver_download_xi.argtypes = [vp, i, vp, vp, vp, vp]
+        L.faldoi_pinned_alloc.argtypes = [C.c_size_t]
+        L.faldoi_pinned_alloc.restype = vp
+        L.faldoi_pinned_free.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -181,6 +188,10 @@ class Solver:
     def upload_ptrs(self, slot, I0, I1, u, Im1=0, lab=0, chi=0):
         """Raw host pointers (e.g. pinned torch tensors' data_ptr()); asynchronous."""
         _check(lib().faldoi_solver_upload(self._h, slot, I0, I1, Im1 or None, lab or None, u, chi or None))
+
+    def set_nltv_fast(self, fast=True):
+        """NLTV handles: opt into the approximate arithmetic mode (faldoi_solver_set_nltv_fast); not bit-exact."""
+        _check(lib().faldoi_solver_set_nltv_fast(self._h, int(bool(fast))))
 
     def run(self, params, npairs=None):
         _check(lib().faldoi_solver_run(self._h, C.byref(params), self.batch if npairs is None else npairs))

@@ -4,7 +4,6 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
-#include <mutex>
 #include <string>
 
 #include "solver.h"
@@ -250,6 +249,7 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
     s->method = method;
     s->B = batch;
     s->g = make_geo(w, h, (w + 31) / 32 * 32, batch);
+    s->nl_parity.assign(batch, 0);
     s->i1_plane = s->g.plane;
     if (sg) {  // row stripe of a taller frame: I1 and its gradients stay full frames (the warp samples any row)
         s->g.y_off = sg->y_off, s->g.hg = sg->hg, s->g.own_lo = sg->own_lo, s->g.own_hi = sg->own_hi;
@@ -393,6 +393,7 @@ extern "C" int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0,
             if ((rc = up2d(s, s->lab + (c * B + slot) * P, lab + c * n))) return rc;
         for (int k = 0; k < 2 * NL_SLOTS; k++)
             FALDOI_CUDA(cudaMemsetAsync(s->dual + (k * B + slot) * P, 0, P * sizeof(float), s->stream));
+        s->nl_parity[slot] = 0;
     }
     if (fam == FAM_OCC) {
         if ((rc = occ_upload(s, slot, Im1, u, chi))) return rc;
@@ -483,6 +484,7 @@ extern "C" int faldoi_solver_upload_raw(faldoi_solver *s, int slot, const float 
                                                         s->lab + (2 * B + slot) * P, g1);
         for (int k = 0; k < 2 * NL_SLOTS; k++)
             FALDOI_CUDA(cudaMemsetAsync(s->dual + (k * B + slot) * P, 0, P * sizeof(float), s->stream));
+        s->nl_parity[slot] = 0;
     }
     if (fam == FAM_OCC) {
         if ((rc = up2d(s, s->occ + (OC_U1 * B + slot) * P, u))) return rc;
@@ -600,41 +602,9 @@ static int make_div_const(faldoi_solver *s, float b, DivConst *out) {
     return FALDOI_OK;
 }
 
-static bool use_tile_kernel() {
-    static const bool v = [] {
-        const char *e = getenv("FALDOI_TV_KERNEL");  // "march" selects the register-marching kernel
-        return !(e && strcmp(e, "march") == 0);
-    }();
-    return v;
-}
-
-template <int DATA>
-static void launch_tv_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs, int R) {
-    if (use_tile_kernel()) {
-        const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
-        tv_tile_kernel<DATA><<<grid, TT_THREADS, sizeof(typename TileSmemFor<DATA>::type) + 128, s->stream>>>(s->maps, a, it);
-        return;
-    }
-    const dim3 block(32, 8);
-    const int cols = (s->g.pitch + 127) / 128;
-    if (R == 4)
-        tv_iter_kernel<4, DATA><<<dim3(cols, (s->g.h + 31) / 32, npairs), block, 0, s->stream>>>(a, it);
-    else if (R == 2)
-        tv_iter_kernel<2, DATA><<<dim3(cols, (s->g.h + 15) / 16, npairs), block, 0, s->stream>>>(a, it);
-    else
-        tv_iter_kernel<1, DATA><<<dim3(cols, (s->g.h + 7) / 8, npairs), block, 0, s->stream>>>(a, it);
-}
-
-// rows per thread: as many as keep >= ~2 waves of 8-warp CTAs on 148 SMs
-static int pick_rows(const Geo &g, int npairs) {
-    if (const char *e = getenv("FALDOI_TV_ROWS")) {  // tuning knob for experiments
-        const int r = atoi(e);
-        if (r == 1 || r == 2 || r == 4) return r;
-    }
-    const long warps1 = (long)((g.pitch + 127) / 128) * g.h * npairs;  // warps at R = 1
-    if (warps1 / 4 >= 148L * 64) return 4;
-    if (warps1 / 2 >= 148L * 64) return 2;
-    return 1;
+static void launch_csad_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs) {
+    const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
+    tv_tile_kernel<DATA_CSAD><<<grid, TT_THREADS, sizeof(typename TileSmemFor<DATA_CSAD>::type) + 128, s->stream>>>(s->maps, a, it);
 }
 
 static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
@@ -664,13 +634,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.l_t = p->lambda * p->theta;
     a.tol2 = p->tol * p->tol;
     if (int rc = make_div_const(s, p->theta, &a.dth)) return rc;
-    const int R = pick_rows(g, npairs);
-    // TVL2 runs two iterations per HBM pass (tv_tile2_kernel) unless FALDOI_TV_T2=0
-    static const bool t2_env = [] {
-        const char *e = getenv("FALDOI_TV_T2");
-        return !(e && e[0] == '0');
-    }();
-    const bool use_t2 = !csad && use_tile_kernel() && t2_env;
+    const bool use_t2 = !csad;  // TVL2: two iterations per HBM pass (tv_tile2_kernel); TV-CSAD: one (tv_tile_kernel<CSAD>)
     if (use_t2) {
         const int need = p->max_iters / 2 + 4;
         if (need > s->t2_stride) {
@@ -759,13 +723,10 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             }
             const int end = (it + CHUNK < p->max_iters) ? it + CHUNK : p->max_iters;
             for (; it < end; it++) {
-                if (csad)
-                    launch_tv_iter<DATA_CSAD>(s, a, it, npairs, R);
-                else
-                    launch_tv_iter<DATA_TVL1>(s, a, it, npairs, R);
+                launch_csad_iter(s, a, it, npairs);
                 s->launches++;
             }
-            count_active_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, npairs, p->max_iters, it - 1, a.tol2,
+            count_active_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->err_sum, 1, npairs, p->max_iters, it - 1, a.tol2,
                                                         (float)(g.w * g.h), s->d_active + (c & 3));
             FALDOI_CUDA(cudaMemcpyAsync(s->h_active + (c & 3), s->d_active + (c & 3), sizeof(int), cudaMemcpyDeviceToHost, s->stream));
             FALDOI_CUDA(cudaEventRecord(s->chunk_ev[c & 3], s->stream));
@@ -823,8 +784,15 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.theta = p->theta;
     a.l_t = p->lambda * p->theta;
     if (int rc = make_div_const(s, p->theta, &a.dth)) return rc;
-    int base_parity = 0;  // every pair runs all max_iters iterations: one parity for the batch
-    FALDOI_CUDA(cudaMemsetAsync(s->parity, 0, (size_t)g.B * sizeof(int), s->stream));
+    // Every pair runs all max_iters iterations, so one ping-pong parity serves the whole batch; it is carried from
+    // run to run (a second run without a fresh upload continues from the first one's result, as the TV family does).
+    // Slots uploaded at different times would disagree -- refuse that instead of reading a stale set.
+    int base_parity = s->nl_parity[0];
+    for (int b = 1; b < npairs; b++)
+        if (s->nl_parity[b] != base_parity) {
+            set_error("faldoi_solver_run (NLTV): the slots of a batch must have been uploaded together (they carry different run histories)");
+            return FALDOI_ERR_ARG;
+        }
     for (int wp = 0; wp < p->warps; wp++) {
         FALDOI_CUDA(cudaMemsetAsync(s->err_sum, 0, (size_t)g.B * p->max_iters * sizeof(double), s->stream));
         WarpArgs wa{};
@@ -866,28 +834,22 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
-        // Default: tiled kernel, exact arithmetic (bit-identical to the reference).  FALDOI_NLTV_FAST=1: tiled kernel
-        // with approximate divisions and paired slot order; FALDOI_NLTV_KERNEL=simple: the first version (one
-        // thread per pixel, plain loads, approximate divisions).
-        static const bool tiled = !(getenv("FALDOI_NLTV_KERNEL") && !strcmp(getenv("FALDOI_NLTV_KERNEL"), "simple"));
-        const bool fast = getenv("FALDOI_NLTV_FAST") && atoi(getenv("FALDOI_NLTV_FAST")) != 0;  // read per run
+        // Exact arithmetic (bit-identical to the reference) unless the caller opted into the approximate mode
+        // (faldoi_solver_set_nltv_fast: approximate divisions, paired slot order).
+        const bool fast = s->nltv_fast;
         const dim3 tgrid((g.pitch + NLT_W - 1) / NLT_W, (g.h + NLT_H - 1) / NLT_H, npairs);
         const size_t tsm = sizeof(NlTileSmem) + 128;
         for (int it = 0; it < p->max_iters; it++) {
-            if (tiled && fast) {
+            if (fast) {
                 if (csad)
                     nltv_tile_kernel<DATA_CSAD, false><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
                 else
                     nltv_tile_kernel<DATA_TVL1, false><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
-            } else if (tiled) {
+            } else {
                 if (csad)
                     nltv_tile_kernel<DATA_CSAD, true><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
                 else
                     nltv_tile_kernel<DATA_TVL1, true><<<tgrid, NLT_THREADS, tsm, s->stream>>>(s->nlmaps, a, it, base_parity);
-            } else if (csad) {
-                nltv_iter_kernel<DATA_CSAD><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
-            } else {
-                nltv_iter_kernel<DATA_TVL1><<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(a, it, base_parity);
             }
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
@@ -898,6 +860,7 @@ static int run_nltv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         s->launches++;
         base_parity = (base_parity + p->max_iters) & 1;
     }
+    for (int b = 0; b < npairs; b++) s->nl_parity[b] = base_parity;
     export_flow_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->state, s->set_stride, s->parity, s->packed, g);
     s->launches++;
     FALDOI_CUDA(cudaGetLastError());
@@ -932,15 +895,6 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
     const Geo g = s->g;
     const dim3 blk(32, 8);
     const dim3 grd = grid2d(g, blk, npairs);
-    const dim3 mgrd((g.w + OM_TW - 1) / OM_TW, (g.h + OM_TH - 1) / OM_TH, npairs);
-    static const bool fused = [] {
-        const char *e = getenv("FALDOI_OCC_FUSED");  // "0" selects the one-sweep-per-launch kernels
-        return !(e && e[0] == '0');
-    }();
-    static const bool rows_variant = [] {
-        const char *e = getenv("FALDOI_OCC_FUSED");  // "smem" selects the shared-memory-resident fused kernels
-        return !(e && strcmp(e, "smem") == 0);
-    }();
     static_assert(OCC_NS <= 4, "the register-resident OCC kernels stage a 4-column apron");
     const dim3 rgrd((g.pitch + OR_W - 1) / OR_W, (g.h + OR_TH - 1) / OR_TH, npairs);
     OccArgs a{};
@@ -972,29 +926,12 @@ static int run_occ(faldoi_solver *s, const faldoi_params *p, int npairs) {
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         for (int it = 0; it < p->max_iters; it++) {
             occ_v_kernel<<<grd, blk, 0, s->stream>>>(a, it);
-            if (fused) {
-                for (int k = 0; k < 24 / OCC_NS; k++) {
-                    if (rows_variant)
-                        occ_xi_rows_kernel<OCC_NS><<<rgrd, 32 * (OR_TH + 2 * OCC_NS), 0, s->stream>>>(a, it, k & 1);
-                    else
-                        occ_xi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1);
-                }
-            } else {
-                for (int k = 0; k < 24; k++) occ_xi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1);
-            }
+            for (int k = 0; k < 24 / OCC_NS; k++)
+                occ_xi_rows_kernel<OCC_NS><<<rgrd, 32 * (OR_TH + 2 * OCC_NS), 0, s->stream>>>(a, it, k & 1);
             occ_u_kernel<<<grd, blk, 0, s->stream>>>(a, it);
-            if (fused) {
-                for (int k = 0; k < 24 / OCC_NS; k++) {
-                    if (rows_variant)
-                        occ_chi_rows_kernel<OCC_NS><<<rgrd, 32 * (OR_TH + 2 * OCC_NS), 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
-                    else
-                        occ_chi_multi_kernel<OCC_NS><<<mgrd, blk, 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
-                }
-                s->launches += 2 + 2 * (24 / OCC_NS);
-            } else {
-                for (int k = 0; k < 24; k++) occ_chi_sweep_kernel<<<grd, blk, 0, s->stream>>>(a, it, k & 1, k == 23);
-                s->launches += 50;
-            }
+            for (int k = 0; k < 24 / OCC_NS; k++)
+                occ_chi_rows_kernel<OCC_NS><<<rgrd, 32 * (OR_TH + 2 * OCC_NS), 0, s->stream>>>(a, it, k & 1, k == 24 / OCC_NS - 1);
+            s->launches += 2 + 2 * (24 / OCC_NS);
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, 0, 0, nullptr, s->log_iters,
@@ -1070,6 +1007,58 @@ extern "C" int faldoi_solver_download(faldoi_solver *s, int slot, float *u, floa
     return faldoi_solver_sync(s);
 }
 
+// Initial / final dual variables of the TV family (methods 0,1,4,5): the xi11..xi22 arrays of tvl2OF / tvcsad_PD.
+extern "C" int faldoi_solver_upload_xi(faldoi_solver *s, int slot, const float *xi11, const float *xi12, const float *xi21,
+                                       const float *xi22) {
+    if (!s || slot < 0 || slot >= s->B || !xi11 || !xi12 || !xi21 || !xi22 || method_family(s->method) != FAM_TV) {
+        set_error("faldoi_solver_upload_xi: bad argument (TV-family handles only)");
+        return FALDOI_ERR_ARG;
+    }
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    const float *src[4] = {xi11, xi12, xi21, xi22};
+    // right after an upload the slot's parity is 0: the initial state lives in set 0
+    for (int k = 0; k < 4; k++)
+        if (int rc = up2d(s, s->state + ((size_t)(ST_XI11 + k) * s->B + slot) * s->g.plane, src[k])) return rc;
+    return FALDOI_OK;
+}
+
+extern "C" int faldoi_solver_download_xi(faldoi_solver *s, int slot, float *xi11, float *xi12, float *xi21, float *xi22) {
+    if (!s || slot < 0 || slot >= s->B || !xi11 || !xi12 || !xi21 || !xi22 || method_family(s->method) != FAM_TV) {
+        set_error("faldoi_solver_download_xi: bad argument (TV-family handles only)");
+        return FALDOI_ERR_ARG;
+    }
+    FALDOI_CUDA(cudaSetDevice(s->device));
+    int par = 0;
+    FALDOI_CUDA(cudaMemcpyAsync(&par, s->parity + slot, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    FALDOI_CUDA(cudaStreamSynchronize(s->stream));
+    float *dst[4] = {xi11, xi12, xi21, xi22};
+    const Geo &g = s->g;
+    for (int k = 0; k < 4; k++)
+        FALDOI_CUDA(cudaMemcpy2DAsync(dst[k], g.w * sizeof(float), s->state + (size_t)par * s->set_stride + ((size_t)(ST_XI11 + k) * s->B + slot) * g.plane,
+                                      g.pitch * sizeof(float), g.w * sizeof(float), g.h, cudaMemcpyDeviceToHost, s->stream));
+    FALDOI_CUDA(cudaStreamSynchronize(s->stream));
+    return FALDOI_OK;
+}
+
+// Page-locked host memory for staging (H2D / D2H copies from it are truly asynchronous and run at full PCIe rate).
+extern "C" void *faldoi_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (!cuda_ok(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+extern "C" void faldoi_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int faldoi_solver_set_nltv_fast(faldoi_solver *s, int fast) {
+    if (!s || method_family(s->method) != FAM_NLTV) {
+        set_error("faldoi_solver_set_nltv_fast: not an NLTV handle");
+        return FALDOI_ERR_ARG;
+    }
+    s->nltv_fast = fast != 0;
+    return FALDOI_OK;
+}
+
 extern "C" float faldoi_solver_last_run_ms(faldoi_solver *s) { return s ? s->last_ms : -1.f; }
 extern "C" float faldoi_solver_last_iter_ms(faldoi_solver *s) { return s ? s->last_iter_ms : -1.f; }
 extern "C" long long faldoi_solver_last_launches(faldoi_solver *s) { return s ? s->launches : -1; }
@@ -1084,35 +1073,42 @@ extern "C" float *faldoi_solver_device_flow(faldoi_solver *s, int slot, int *pit
 // one-call host entry and the per-solver mirrors
 // ---------------------------------------------------------------------------
 namespace {
-struct CacheKey {
-    int device, w, h, method;
-};
-std::mutex g_cache_mu;
-faldoi_solver *g_cached = nullptr;
-CacheKey g_cached_key{-1, 0, 0, -1};
-}  // namespace
-
-// A single-pair handle is kept alive between calls with the same (device, w, h,
-// method) so a sequence of pairs does not pay cudaMalloc per call.
-static int cached_solver(int device, int w, int h, int method, faldoi_solver **out) {
-    if (g_cached && g_cached_key.device == device && g_cached_key.w == w && g_cached_key.h == h &&
-        g_cached_key.method == method) {
-        *out = g_cached;
+// Single-pair handles behind the one-call entries, kept alive between calls so that a sequence of pairs does not
+// pay cudaMalloc per call.  The cache is PER HOST THREAD (a few entries, least recently used first out): threads
+// driving different GPUs -- or the same one -- never share a handle, so the entries need no lock and eight host
+// threads on eight GPUs run concurrently (re-entrant per device).
+struct SolverCache {
+    struct Entry {
+        int device, w, h, method;
+        faldoi_solver *s;
+    };
+    std::vector<Entry> e;
+    ~SolverCache() {
+        for (Entry &x : e) faldoi_solver_destroy(x.s);
+    }
+    int get(int device, int w, int h, int method, faldoi_solver **out) {
+        for (size_t i = 0; i < e.size(); i++)
+            if (e[i].device == device && e[i].w == w && e[i].h == h && e[i].method == method) {
+                const Entry hit = e[i];
+                e.erase(e.begin() + i);
+                e.push_back(hit);
+                *out = hit.s;
+                return FALDOI_OK;
+            }
+        if (e.size() >= 3) {
+            faldoi_solver_destroy(e.front().s);
+            e.erase(e.begin());
+        }
+        faldoi_solver *s = nullptr;
+        const int rc = faldoi_solver_create(&s, device, w, h, method, 1);
+        if (rc != FALDOI_OK) return rc;
+        e.push_back(Entry{device, w, h, method, s});
+        *out = s;
         return FALDOI_OK;
     }
-    if (g_cached) {
-        faldoi_solver_destroy(g_cached);
-        g_cached = nullptr;
-    }
-    int rc = faldoi_solver_create(&g_cached, device, w, h, method, 1);
-    if (rc != FALDOI_OK) {
-        g_cached = nullptr;
-        return rc;
-    }
-    g_cached_key = CacheKey{device, w, h, method};
-    *out = g_cached;
-    return FALDOI_OK;
-}
+};
+thread_local SolverCache t_cache;
+}  // namespace
 
 extern "C" int faldoi_global_solve(int device, const faldoi_params *p, int w, int h, const float *I0, const float *I1,
                                    const float *Im1, const float *lab, float *u, float *chi, faldoi_log *log) {
@@ -1120,9 +1116,8 @@ extern "C" int faldoi_global_solve(int device, const faldoi_params *p, int w, in
         set_error("faldoi_global_solve: null argument");
         return FALDOI_ERR_ARG;
     }
-    std::lock_guard<std::mutex> lock(g_cache_mu);
     faldoi_solver *s = nullptr;
-    int rc = cached_solver(device, w, h, p->method, &s);
+    int rc = t_cache.get(device, w, h, p->method, &s);
     if (rc != FALDOI_OK) return rc;
     if ((rc = faldoi_solver_upload(s, 0, I0, I1, Im1, lab, u, chi)) != FALDOI_OK) return rc;
     if ((rc = faldoi_solver_run(s, p, 1)) != FALDOI_OK) return rc;
@@ -1135,9 +1130,8 @@ extern "C" int faldoi_global_solve_raw(int device, const faldoi_params *p, int w
         set_error("faldoi_global_solve_raw: null argument");
         return FALDOI_ERR_ARG;
     }
-    std::lock_guard<std::mutex> lock(g_cache_mu);
     faldoi_solver *s = nullptr;
-    int rc = cached_solver(device, w, h, p->method, &s);
+    int rc = t_cache.get(device, w, h, p->method, &s);
     if (rc != FALDOI_OK) return rc;
     if ((rc = faldoi_solver_upload_raw(s, 0, i0, i1, im1, pd, u, chi)) != FALDOI_OK) return rc;
     if ((rc = faldoi_solver_run(s, p, 1)) != FALDOI_OK) return rc;
@@ -1149,40 +1143,50 @@ static void print_log(const faldoi_params &p, const faldoi_log &log, FILE *f, co
 }
 
 static int solve_split(const faldoi_params &p, int nx, int ny, const float *I0, const float *I1, const float *Im1,
-                       const float *lab, float *u1, float *u2, float *chi, int verbose, FILE *vf, const char *fmt) {
+                       const float *lab, float *u1, float *u2, float *chi, float *const xi[4], int verbose, FILE *vf, const char *fmt) {
     const size_t n = (size_t)nx * ny;
     std::vector<float> u(2 * n);
     memcpy(u.data(), u1, n * sizeof(float));
     memcpy(u.data() + n, u2, n * sizeof(float));
     faldoi_log log{};
-    int rc = faldoi_global_solve(0, &p, nx, ny, I0, I1, Im1, lab, u.data(), chi, &log);
+    faldoi_solver *s = nullptr;
+    int rc = t_cache.get(0, nx, ny, p.method, &s);
     if (rc != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_upload(s, 0, I0, I1, Im1, lab, u.data(), chi)) != FALDOI_OK) return rc;
+    const bool with_xi = xi && xi[0] && xi[1] && xi[2] && xi[3];
+    if (with_xi && (rc = faldoi_solver_upload_xi(s, 0, xi[0], xi[1], xi[2], xi[3])) != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_run(s, &p, 1)) != FALDOI_OK) return rc;
+    if ((rc = faldoi_solver_download(s, 0, u.data(), chi, &log)) != FALDOI_OK) return rc;
+    if (with_xi && (rc = faldoi_solver_download_xi(s, 0, xi[0], xi[1], xi[2], xi[3])) != FALDOI_OK) return rc;
     memcpy(u1, u.data(), n * sizeof(float));
     memcpy(u2, u.data() + n, n * sizeof(float));
     if (verbose) print_log(p, log, vf, fmt);
     return FALDOI_OK;
 }
 
-// The reference's xi arguments are caller-owned scratch that main() zeroes right
-// before the call (src/global_faldoi.cpp:2116-2121) and never reads afterwards;
-// the GPU keeps the duals in HBM, so xi11..xi22 are accepted and left untouched.
-extern "C" int faldoi_tvl2OF(const float *I0, float *I1, float *u1, float *u2, float *, float *, float *, float *,
+// The reference's xi arguments are caller-owned arrays that the solver reads as the initial dual variables and
+// updates in place (src/global_faldoi.cpp:556-573, 735; main() zeroes them right before the call, :2116-2121).
+// The mirrors honour that: the four arrays are uploaded as the initial duals and hold the final duals on return
+// (a warm-starting caller sees what it would see from the reference).  Passing NULL for them starts from zero.
+extern "C" int faldoi_tvl2OF(const float *I0, float *I1, float *u1, float *u2, float *xi11, float *xi12, float *xi21, float *xi22,
                              float lambda, float theta, float tau, float tol_OF, int nx, int ny, int warps,
                              int verbose) {
     faldoi_params p;
     faldoi_default_params(FALDOI_M_TVL1, 400, &p);
     p.lambda = lambda, p.theta = theta, p.tau = tau, p.tol = tol_OF, p.warps = warps;
-    return solve_split(p, nx, ny, I0, I1, nullptr, nullptr, u1, u2, nullptr, verbose, stderr,
+    float *const xi[4] = {xi11, xi12, xi21, xi22};
+    return solve_split(p, nx, ny, I0, I1, nullptr, nullptr, u1, u2, nullptr, xi, verbose, stderr,
                        "Warping: %d,Iter: %d Error: %f\n");
 }
 
-extern "C" int faldoi_tvcsad_PD(const float *I0, float *I1, float *, float *, float *, float *, float lambda,
+extern "C" int faldoi_tvcsad_PD(const float *I0, float *I1, float *xi11, float *xi12, float *xi21, float *xi22, float lambda,
                                 float theta, float tau, float tol_OF, int nx, int ny, int warps, int verbose,
                                 float *u1, float *u2) {
     faldoi_params p;
     faldoi_default_params(FALDOI_M_TVCSAD, 400, &p);
     p.lambda = lambda, p.theta = theta, p.tau = tau, p.tol = tol_OF, p.warps = warps;
-    return solve_split(p, nx, ny, I0, I1, nullptr, nullptr, u1, u2, nullptr, verbose, stderr,
+    float *const xi[4] = {xi11, xi12, xi21, xi22};
+    return solve_split(p, nx, ny, I0, I1, nullptr, nullptr, u1, u2, nullptr, xi, verbose, stderr,
                        "Warping: %d,Iter: %d Error: %f\n");
 }
 
@@ -1195,7 +1199,7 @@ extern "C" int faldoi_nltvl1_PD(const float *I0, float *I1, float *a, int pd, fl
     faldoi_params p;
     faldoi_default_params(FALDOI_M_NLTVL1, 400, &p);
     p.lambda = lambda, p.theta = theta, p.tau = tau, p.warps = warps;
-    return solve_split(p, w, h, I0, I1, nullptr, a, u1, u2, nullptr, verbose, stdout, "Warping: %d,Iter: %d Error: %f\n");
+    return solve_split(p, w, h, I0, I1, nullptr, a, u1, u2, nullptr, nullptr, verbose, stdout, "Warping: %d,Iter: %d Error: %f\n");
 }
 
 extern "C" int faldoi_nltvcsad_PD(const float *I0, float *I1, float *a, int pd, float lambda, float theta, float tau,
@@ -1207,7 +1211,7 @@ extern "C" int faldoi_nltvcsad_PD(const float *I0, float *I1, float *a, int pd, 
     faldoi_params p;
     faldoi_default_params(FALDOI_M_NLTVCSAD, 400, &p);
     p.lambda = lambda, p.theta = theta, p.tau = tau, p.warps = warps;
-    return solve_split(p, w, h, I0, I1, nullptr, a, u1, u2, nullptr, verbose, stdout, "Warping: %d,Iter: %d Error: %f\n");
+    return solve_split(p, w, h, I0, I1, nullptr, a, u1, u2, nullptr, nullptr, verbose, stdout, "Warping: %d,Iter: %d Error: %f\n");
 }
 
 extern "C" int faldoi_guided_tvl2coupled_occ(const float *I0, const float *I1, const float *I_1, float *u1, float *u2,
@@ -1216,7 +1220,7 @@ extern "C" int faldoi_guided_tvl2coupled_occ(const float *I0, const float *I1, c
         set_error("faldoi_guided_tvl2coupled_occ: params.method must be 8");
         return FALDOI_ERR_ARG;
     }
-    return solve_split(*p, nx, ny, I0, I1, I_1, nullptr, u1, u2, chi, verbose, stdout,
+    return solve_split(*p, nx, ny, I0, I1, I_1, nullptr, u1, u2, chi, nullptr, verbose, stdout,
                        "Warping: %d, Iter: %d Error: %f\n");
 }
 

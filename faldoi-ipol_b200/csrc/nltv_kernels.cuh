@@ -95,135 +95,4 @@ struct NlArgs {
     DivConst dth;  // division by theta
 };
 
-// One fused NLTV iteration (:1249-1301 / :1729-1777): data-term v, dual update
-// (ofnltv_getD :1127-1174), non-local divergence (:1056-1079) and primal step
-// (ofnltv_getP :1090-1120, note +div) in one pass.  The neighbour's reciprocal
-// dual P_new[23-s](q) that the divergence needs is recomputed from
-// P_old[23-s](q) instead of being re-read after a grid-wide barrier; its
-// weight wgt[23-s](q) equals wgt[s](p) bit for bit (symmetric formula).
-// Launch `it` reads set (it&1) and writes set (it&1)^1: NLTV always runs all
-// max_iters iterations (:1249), so the parity is the same for every pair.
-template <int DATA>
-__global__ void __launch_bounds__(256, 4) nltv_iter_kernel(NlArgs a, int it, int base_parity) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int b = blockIdx.z;
-    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
-    const bool inimg = (x < w && y < h);
-    double esum = 0.0;
-    if (inimg) {
-        const int par = (base_parity + it) & 1;
-        const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane, off = (size_t)b * plane;
-        const float *sin = a.state + (size_t)par * a.set_stride + off;
-        float *sout = a.state + (size_t)(par ^ 1) * a.set_stride + off;
-        const float *din = a.dual + (size_t)par * a.dual_set_stride + off;
-        float *dout = a.dual + (size_t)(par ^ 1) * a.dual_set_stride + off;
-        const int p = y * pitch + x;
-        const float tau = a.tau, l_t = a.l_t;
-        const float u1 = sin[ST_U1 * ks + p], u2 = sin[ST_U2 * ks + p];
-        const float c1 = sin[ST_UB1 * ks + p], c2 = sin[ST_UB2 * ks + p];
-        const float ix = a.Ix[off + p], iy = a.Iy[off + p];
-        const float wtp = a.wt[off + p];
-
-        // ---- data term ----
-        float v1, v2;
-        if (DATA == DATA_TVL1) {
-            const float grad = ix * ix + iy * iy;
-            const float rho = a.rho_c[off + p] + (ix * u1 + iy * u2);
-            float e1, e2;
-            if (rho < -l_t * grad) {
-                e1 = l_t * ix;
-                e2 = l_t * iy;
-            } else if (rho > l_t * grad) {
-                e1 = -l_t * ix;
-                e2 = -l_t * iy;
-            } else if (grad_is_zero(grad)) {
-                e1 = e2 = 0.f;
-            } else {
-                const float fi = -rho / grad;
-                e1 = fi * ix;
-                e2 = fi * iy;
-            }
-            v1 = u1 + e1;
-            v2 = u2 + e2;
-        } else {
-            v1 = u1;
-            v2 = u2;
-            const float sc = a.scale[off + p];
-            if (sc != 0.f) {  // 0 marks grad <= GRAD_IS_ZERO (:1734)
-                const float s = (ix * u1 + iy * u2) / sc;
-                const int np = csad_count(x, y, w, h);
-                const float med = csad_select(a.blk, a.sep, a.g, b, y, x, np, s, l_t, sc);
-                v1 = csad_apply(u1, ix, med, sc);
-                v2 = csad_apply(u2, iy, med, sc);
-            }
-        }
-
-        // ---- dual update + non-local divergence ----
-        // Pixels at least 2 away from every frame border (all 24 neighbours exist) take a loop without
-        // bounds tests; 1/wt is formed once per pixel (the NLTV models are tolerance-level, see NL_DIV).
-        float dP = 0.f, dQ = 0.f;
-        const float rwtp = NL_DIV(1.f, wtp);
-        const float *ub1p = sin + ST_UB1 * ks, *ub2p = sin + ST_UB2 * ks;
-        const float *wtb = a.wt + off;
-        auto slot = [&](int s, int q) {
-            const float wv = a.wgt[(size_t)s * ks + off + p];
-            const float q1 = ub1p[q], q2 = ub2p[q];
-            const float rwtq = NL_DIV(1.f, wtb[q]);
-            const float t1 = wv * (c1 - q1), t2 = wv * (c2 - q2);
-            // own dual, slot s
-            const float g1 = t1 * rwtp, g2 = t2 * rwtp;
-            const float Pn = NL_DIV(din[(size_t)s * ks + p] + tau * g1, 1 + tau * fabsf(g1));
-            const float Qn = NL_DIV(din[(size_t)(NL_SLOTS + s) * ks + p] + tau * g2, 1 + tau * fabsf(g2));
-            dout[(size_t)s * ks + p] = Pn;
-            dout[(size_t)(NL_SLOTS + s) * ks + p] = Qn;
-            // neighbour's reciprocal dual, slot 23-s at q (its difference is the negated one)
-            const int rs = NL_SLOTS - 1 - s;
-            const float h1 = -t1 * rwtq, h2 = -t2 * rwtq;
-            const float Pr = NL_DIV(din[(size_t)rs * ks + q] + tau * h1, 1 + tau * fabsf(h1));
-            const float Qr = NL_DIV(din[(size_t)(NL_SLOTS + rs) * ks + q] + tau * h2, 1 + tau * fabsf(h2));
-            dP += wv * (Pn - Pr);
-            dQ += wv * (Qn - Qr);
-        };
-        if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {
-#pragma unroll
-            for (int s = 0; s < NL_SLOTS; s++) {
-                int k, l;
-                nl_slot_offset(s, k, l);
-                slot(s, p + k * pitch + l);
-            }
-        } else {
-#pragma unroll
-            for (int s = 0; s < NL_SLOTS; s++) {
-                int k, l;
-                nl_slot_offset(s, k, l);
-                const int r = y + k, c = x + l;
-                if (c >= 0 && c < w && r >= 0 && r < h) slot(s, r * pitch + c);
-            }
-        }
-        dP *= rwtp;
-        dQ *= rwtp;
-
-        // ---- primal step (+div) and extrapolation ----
-        const float o1 = u1 - tau * (dP + div_const(u1 - v1, a.dth));
-        const float o2 = u2 - tau * (dQ + div_const(u2 - v2, a.dth));
-        esum = (double)((o1 - u1) * (o1 - u1) + (o2 - u2) * (o2 - u2));
-        sout[ST_U1 * ks + p] = o1;
-        sout[ST_U2 * ks + p] = o2;
-        sout[ST_UB1 * ks + p] = 2 * o1 - u1;
-        sout[ST_UB2 * ks + p] = 2 * o2 - u2;
-    }
-    // printed error only (the exit test is commented out upstream, :1248)
-    __shared__ double red[8];
-    esum = warp_sum(esum);
-    const int wid = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
-    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) red[wid] = esum;
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        double t = 0.0;
-        for (int i = 0; i < (int)(blockDim.x * blockDim.y / 32); i++) t += red[i];
-        atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
-    }
-}
-
 }  // namespace faldoi

@@ -175,43 +175,6 @@ __device__ __forceinline__ float occ_div_gxi(const float *__restrict__ g, const 
     return div_bc(a_c, a_l, b_c, b_u, x, y, w, h);
 }
 
-// one Chambolle sweep for xi (:340-392), set `src` -> set `src^1`
-__global__ void __launch_bounds__(256) occ_xi_sweep_kernel(OccArgs a, int it, int src) {
-    const int b = blockIdx.z;
-    if (!occ_active(a, b, it)) return;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
-    if (x >= w || y >= h) return;
-    const int p = y * pitch + x;
-    const float *g = occ_plane(a, OC_G, b);
-    const float *xin = occ_plane(a, src ? OC_XI1 : OC_XI0, b);
-    float *xout = occ_plane(a, src ? OC_XI0 : OC_XI1, b);
-    const size_t ks = (size_t)a.g.B * a.g.plane;
-    const float theta = a.theta, tt = a.tau_theta;
-    const float gp = g[p];
-#pragma unroll
-    for (int c = 0; c < 2; c++) {  // c = 0: (xi11, xi12, v1, k1);  c = 1: (xi21, xi22, v2, k2)
-        const float *xa = xin + (size_t)(2 * c) * ks, *xb = xin + (size_t)(2 * c + 1) * ks;
-        const float *v = occ_plane(a, OC_V1 + c, b), *k = occ_plane(a, OC_K1 + c, b);
-        // vi = v + theta*div(g xi) + theta*beta*chi_grad   (:353-354) at p, p+1, p+pitch
-        const float vi_c = v[p] + theta * occ_div_gxi(g, xa, xb, x, y, w, h, pitch) + k[p];
-        float gx = 0.f, gy = 0.f;
-        if (x < w - 1) {
-            const float vi_r = v[p + 1] + theta * occ_div_gxi(g, xa, xb, x + 1, y, w, h, pitch) + k[p + 1];
-            gx = vi_r - vi_c;
-        }
-        if (y < h - 1) {
-            const float vi_d = v[p + pitch] + theta * occ_div_gxi(g, xa, xb, x, y + 1, w, h, pitch) + k[p + pitch];
-            gy = vi_d - vi_c;
-        }
-        const float e1 = gp * gx, e2 = gp * gy;
-        const float nrm = sqrt_or_zero(e1 * e1 + e2 * e2);
-        xout[(size_t)(2 * c) * ks + p] = (xa[p] + tt * e1) / (1 + tt * nrm);
-        xout[(size_t)(2 * c + 1) * ks + p] = (xb[p] + tt * e2) / (1 + tt * nrm);
-    }
-}
-
 // final divergence, u-update, |du|^2, F and G (:394-406, :726-751)
 __global__ void __launch_bounds__(256) occ_u_kernel(OccArgs a, int it) {
     const int b = blockIdx.z;
@@ -250,252 +213,6 @@ __global__ void __launch_bounds__(256) occ_u_kernel(OccArgs a, int it) {
         float m = red[0];
         for (int i = 1; i < (int)(blockDim.x * blockDim.y / 32); i++) m = fmaxf(m, red[i]);
         atomicMax(a.err_max + (size_t)b * a.max_iters + it, __float_as_uint(m));
-    }
-}
-
-// eta_new at pixel (x,y) from the old eta and the current chi (:439-452)
-__device__ __forceinline__ void occ_eta_new(const float *__restrict__ eta1, const float *__restrict__ eta2,
-                                            const float *__restrict__ chi, const float *__restrict__ g, float mte, int x,
-                                            int y, int w, int h, int pitch, float &o1, float &o2) {
-    const int p = y * pitch + x;
-    const float c = chi[p];
-    const float chix = (x < w - 1) ? chi[p + 1] - c : 0.f;
-    const float chiy = (y < h - 1) ? chi[p + pitch] - c : 0.f;
-    const float e1 = eta1[p] + mte * g[p] * chix;
-    const float e2 = eta2[p] + mte * g[p] * chiy;
-    const float ne = sqrtf(e1 * e1 + e2 * e2);
-    if (ne <= 1) {
-        o1 = e1;
-        o2 = e2;
-    } else {
-        o1 = e1 / ne;
-        o2 = e2 / ne;
-    }
-}
-
-// one primal-dual sweep for chi (:431-474); the last one also thresholds (:476-483)
-__global__ void __launch_bounds__(256) occ_chi_sweep_kernel(OccArgs a, int it, int src, int last) {
-    const int b = blockIdx.z;
-    if (!occ_active(a, b, it)) return;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
-    if (x >= w || y >= h) return;
-    const int p = y * pitch + x;
-    const float *g = occ_plane(a, OC_G, b);
-    const float *e1 = occ_plane(a, src ? OC_ETA1 : OC_ETA0, b), *e2 = e1 + (size_t)a.g.B * a.g.plane;
-    float *o1 = occ_plane(a, src ? OC_ETA0 : OC_ETA1, b), *o2 = o1 + (size_t)a.g.B * a.g.plane;
-    const float *chi = occ_plane(a, src ? OC_CHI1 : OC_CHI0, b);
-    float *chio = occ_plane(a, src ? OC_CHI0 : OC_CHI1, b);
-    const float mte = a.mu * a.tau_eta;
-    float n1, n2, l1 = 0.f, l2 = 0.f, t1 = 0.f, t2 = 0.f;
-    occ_eta_new(e1, e2, chi, g, mte, x, y, w, h, pitch, n1, n2);
-    if (x > 0) occ_eta_new(e1, e2, chi, g, mte, x - 1, y, w, h, pitch, l1, l2);
-    if (y > 0) occ_eta_new(e1, e2, chi, g, mte, x, y - 1, w, h, pitch, t1, t2);
-    o1[p] = n1;
-    o2[p] = n2;
-    const float a_c = g[p] * n1, b_c = g[p] * n2;
-    const float a_l = (x > 0) ? g[p - 1] * l1 : 0.f;
-    const float b_u = (y > 0) ? g[p - pitch] * t2 : 0.f;
-    const float dge = div_bc(a_c, a_l, b_c, b_u, x, y, w, h);
-    const float div_u = 0.f;  // target definition
-    const float cn = chi[p] + a.tau_chi * (a.mu * dge - a.beta * div_u - occ_plane(a, OC_F, b)[p] - occ_plane(a, OC_GG, b)[p]);
-    const float lo = (cn < 1) ? cn : 1;
-    float c = (lo > 0) ? lo : 0;
-    if (last) c = ((double)c > 0.6) ? 1.f : 0.f;
-    chio[p] = c;
-}
-
-// ---------------------------------------------------------------------------
-// Temporally blocked sweeps.  A xi sweep / chi sweep has a radius-1 dependency, so NS
-// consecutive sweeps of a 32x16 tile only need the tile plus an NS-pixel apron: the CTA
-// stages that region in shared memory, runs NS sweeps there (the region that is still exact
-// shrinks by one ring per sweep, frame borders do not shrink) and writes the tile back once.
-// HBM traffic per sweep drops by ~NS/1.3; every pixel value is produced by the same
-// expression as in the one-sweep kernels above, so results are bit-identical.
-// ---------------------------------------------------------------------------
-enum { OM_TW = 32, OM_TH = 16 };
-
-struct OmRegion {  // half-open global pixel ranges
-    int x_lo, x_hi, y_lo, y_hi;
-};
-__device__ __forceinline__ OmRegion om_region(int x0, int y0, int ring, int w, int h) {
-    OmRegion r;
-    r.x_lo = max(0, x0 - ring);
-    r.x_hi = min(w, x0 + OM_TW + ring);
-    r.y_lo = max(0, y0 - ring);
-    r.y_hi = min(h, y0 + OM_TH + ring);
-    return r;
-}
-
-// NS Chambolle sweeps for xi (same arithmetic as occ_xi_sweep_kernel), set `src` -> the other set
-// (always: neighbouring CTAs read their aprons from `src` while this one writes its tile)
-template <int NS>
-__global__ void __launch_bounds__(256) occ_xi_multi_kernel(OccArgs a, int it, int src) {
-    constexpr int SW = OM_TW + 2 * NS, SH = OM_TH + 2 * NS, SN = SW * SH;
-    __shared__ float sx[4][SN], sg[SN], sv[2][SN], sk[2][SN], svi[2][SN];
-    const int b = blockIdx.z;
-    if (!occ_active(a, b, it)) return;
-    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
-    const int x0 = blockIdx.x * OM_TW, y0 = blockIdx.y * OM_TH;
-    const int ox = x0 - NS, oy = y0 - NS;  // global coords of smem (0,0)
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const size_t ks = (size_t)a.g.B * a.g.plane;
-    const float *g = occ_plane(a, OC_G, b);
-    const float *xin = occ_plane(a, src ? OC_XI1 : OC_XI0, b);
-    float *xout = occ_plane(a, src ? OC_XI0 : OC_XI1, b);
-    const float *v1 = occ_plane(a, OC_V1, b), *v2 = occ_plane(a, OC_V2, b);
-    const float *k1 = occ_plane(a, OC_K1, b), *k2 = occ_plane(a, OC_K2, b);
-    const float theta = a.theta, tt = a.tau_theta;
-
-    const OmRegion E0 = om_region(x0, y0, NS, w, h);
-    for (int i = tid; i < SN; i += 256) {
-        const int lx = i % SW, ly = i / SW, gx = ox + lx, gy = oy + ly;
-        const bool in = gx >= E0.x_lo && gx < E0.x_hi && gy >= E0.y_lo && gy < E0.y_hi;
-        const int p = gy * pitch + gx;
-#pragma unroll
-        for (int c = 0; c < 4; c++) sx[c][i] = in ? xin[(size_t)c * ks + p] : 0.f;
-        sg[i] = in ? g[p] : 0.f;
-        sv[0][i] = in ? v1[p] : 0.f;
-        sv[1][i] = in ? v2[p] : 0.f;
-        sk[0][i] = in ? k1[p] : 0.f;
-        sk[1][i] = in ? k2[p] : 0.f;
-    }
-    __syncthreads();
-
-#pragma unroll 1
-    for (int s = 0; s < NS; s++) {
-        const OmRegion E = om_region(x0, y0, NS - s, w, h);       // xi exact here at sweep start
-        const OmRegion En = om_region(x0, y0, NS - s - 1, w, h);  // xi exact here after this sweep
-        // phase 1: vi = v + theta*div(g xi) + theta*beta*grad(chi) where its left / upper neighbours are exact
-        const int vx_lo = E.x_lo + (E.x_lo > 0), vy_lo = E.y_lo + (E.y_lo > 0);
-        for (int l = tid; l < SN; l += 256) {  // SW is a compile-time constant: cheap index math, region test per pixel
-            const int gx = ox + l % SW, gy = oy + l / SW;
-            if (gx < vx_lo || gx >= E.x_hi || gy < vy_lo || gy >= E.y_hi) continue;
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const float *xa = sx[2 * c], *xb = sx[2 * c + 1];
-                const float a_c = sg[l] * xa[l], b_c = sg[l] * xb[l];
-                const float a_l = (gx > 0) ? sg[l - 1] * xa[l - 1] : 0.f;
-                const float b_u = (gy > 0) ? sg[l - SW] * xb[l - SW] : 0.f;
-                svi[c][l] = sv[c][l] + theta * div_bc(a_c, a_l, b_c, b_u, gx, gy, w, h) + sk[c][l];
-            }
-        }
-        __syncthreads();
-        // phase 2: xi <- (xi + t g grad(vi)) / (1 + t |g grad(vi)|) on the next exact region
-        for (int l = tid; l < SN; l += 256) {
-            const int gx = ox + l % SW, gy = oy + l / SW;
-            if (gx < En.x_lo || gx >= En.x_hi || gy < En.y_lo || gy >= En.y_hi) continue;
-            const float gp = sg[l];
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const float vi_c = svi[c][l];
-                const float gxv = (gx < w - 1) ? svi[c][l + 1] - vi_c : 0.f;
-                const float gyv = (gy < h - 1) ? svi[c][l + SW] - vi_c : 0.f;
-                const float e1 = gp * gxv, e2 = gp * gyv;
-                const float nrm = sqrt_or_zero(e1 * e1 + e2 * e2);
-                float q1 = sx[2 * c][l] + tt * e1, q2 = sx[2 * c + 1][l] + tt * e2;
-                div2_shared(q1, q2, 1 + tt * nrm);
-                sx[2 * c][l] = q1;
-                sx[2 * c + 1][l] = q2;
-            }
-        }
-        __syncthreads();
-    }
-    const OmRegion I = om_region(x0, y0, 0, w, h);
-    const int iw = I.x_hi - I.x_lo, ih = I.y_hi - I.y_lo;
-    for (int i = tid; i < iw * ih; i += 256) {
-        const int gx = I.x_lo + i % iw, gy = I.y_lo + i / iw;
-        const int l = (gy - oy) * SW + (gx - ox), p = gy * pitch + gx;
-#pragma unroll
-        for (int c = 0; c < 4; c++) xout[(size_t)c * ks + p] = sx[c][l];
-    }
-}
-
-// NS primal-dual sweeps for chi (same arithmetic as occ_chi_sweep_kernel); `last` thresholds after the final sweep
-template <int NS>
-__global__ void __launch_bounds__(256) occ_chi_multi_kernel(OccArgs a, int it, int src, int last) {
-    constexpr int SW = OM_TW + 2 * NS, SH = OM_TH + 2 * NS, SN = SW * SH;
-    __shared__ float se[2][SN], sc[SN], sg[SN], sF[SN], sG[SN];
-    const int b = blockIdx.z;
-    if (!occ_active(a, b, it)) return;
-    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
-    const int x0 = blockIdx.x * OM_TW, y0 = blockIdx.y * OM_TH;
-    const int ox = x0 - NS, oy = y0 - NS;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const size_t ks = (size_t)a.g.B * a.g.plane;
-    const int dst = src ^ 1;
-    const float *g = occ_plane(a, OC_G, b);
-    const float *e_in = occ_plane(a, src ? OC_ETA1 : OC_ETA0, b);
-    float *e_out = occ_plane(a, dst ? OC_ETA1 : OC_ETA0, b);
-    const float *chi_in = occ_plane(a, src ? OC_CHI1 : OC_CHI0, b);
-    float *chi_out = occ_plane(a, dst ? OC_CHI1 : OC_CHI0, b);
-    const float *F = occ_plane(a, OC_F, b), *G = occ_plane(a, OC_GG, b);
-    const float mte = a.mu * a.tau_eta;
-
-    const OmRegion E0 = om_region(x0, y0, NS, w, h);
-    for (int i = tid; i < SN; i += 256) {
-        const int lx = i % SW, ly = i / SW, gx = ox + lx, gy = oy + ly;
-        const bool in = gx >= E0.x_lo && gx < E0.x_hi && gy >= E0.y_lo && gy < E0.y_hi;
-        const int p = gy * pitch + gx;
-        se[0][i] = in ? e_in[p] : 0.f;
-        se[1][i] = in ? e_in[ks + p] : 0.f;
-        sc[i] = in ? chi_in[p] : 0.f;
-        sg[i] = in ? g[p] : 0.f;
-        sF[i] = in ? F[p] : 0.f;
-        sG[i] = in ? G[p] : 0.f;
-    }
-    __syncthreads();
-
-#pragma unroll 1
-    for (int s = 0; s < NS; s++) {
-        const OmRegion E = om_region(x0, y0, NS - s, w, h);       // eta, chi exact here at sweep start
-        const OmRegion En = om_region(x0, y0, NS - s - 1, w, h);  // ... and here after this sweep
-        // phase 1: eta <- proj(eta + mu tau_eta g grad(chi)) where chi's right / lower neighbours are exact
-        const int ex_hi = E.x_hi - (E.x_hi < w), ey_hi = E.y_hi - (E.y_hi < h);
-        for (int l = tid; l < SN; l += 256) {
-            const int gx = ox + l % SW, gy = oy + l / SW;
-            if (gx < E.x_lo || gx >= ex_hi || gy < E.y_lo || gy >= ey_hi) continue;
-            const float c = sc[l];
-            const float chix = (gx < w - 1) ? sc[l + 1] - c : 0.f;
-            const float chiy = (gy < h - 1) ? sc[l + SW] - c : 0.f;
-            const float e1 = se[0][l] + mte * sg[l] * chix;
-            const float e2 = se[1][l] + mte * sg[l] * chiy;
-            const float ne = sqrtf(e1 * e1 + e2 * e2);
-            if (ne <= 1) {
-                se[0][l] = e1;
-                se[1][l] = e2;
-            } else {
-                se[0][l] = e1 / ne;
-                se[1][l] = e2 / ne;
-            }
-        }
-        __syncthreads();
-        // phase 2: chi <- clamp(chi + tau_chi (mu div(g eta) - beta div_u - F - G), 0, 1)
-        for (int l = tid; l < SN; l += 256) {
-            const int gx = ox + l % SW, gy = oy + l / SW;
-            if (gx < En.x_lo || gx >= En.x_hi || gy < En.y_lo || gy >= En.y_hi) continue;
-            const float a_c = sg[l] * se[0][l], b_c = sg[l] * se[1][l];
-            const float a_l = (gx > 0) ? sg[l - 1] * se[0][l - 1] : 0.f;
-            const float b_u = (gy > 0) ? sg[l - SW] * se[1][l - SW] : 0.f;
-            const float dge = div_bc(a_c, a_l, b_c, b_u, gx, gy, w, h);
-            const float div_u = 0.f;  // target definition
-            const float cn = sc[l] + a.tau_chi * (a.mu * dge - a.beta * div_u - sF[l] - sG[l]);
-            const float lo = (cn < 1) ? cn : 1;
-            sc[l] = (lo > 0) ? lo : 0;
-        }
-        __syncthreads();
-    }
-    const OmRegion I = om_region(x0, y0, 0, w, h);
-    const int iw = I.x_hi - I.x_lo, ih = I.y_hi - I.y_lo;
-    for (int i = tid; i < iw * ih; i += 256) {
-        const int gx = I.x_lo + i % iw, gy = I.y_lo + i / iw;
-        const int l = (gy - oy) * SW + (gx - ox), p = gy * pitch + gx;
-        e_out[p] = se[0][l];
-        e_out[ks + p] = se[1][l];
-        float c = sc[l];
-        if (last) c = ((double)c > 0.6) ? 1.f : 0.f;
-        chi_out[p] = c;
     }
 }
 

@@ -52,6 +52,8 @@ struct faldoi_solver {
     float *lab = nullptr, *wgt = nullptr, *wt = nullptr, *rwt = nullptr, *dual = nullptr;
     faldoi::NlTileMaps nlmaps{};  // TMA descriptors of nltv_tile_kernel
     size_t dual_set_stride = 0;
+    std::vector<int> nl_parity;  // NLTV: ping-pong set that holds each slot's current state (host copy; all pairs run all iterations)
+    bool nltv_fast = false;  // faldoi_solver_set_nltv_fast: approximate divisions + paired slot order (not bit-exact)
     // device-side preprocessing (upload_raw): staging for the raw frames, scratch planes, min/max keys
     float *raw_stage = nullptr;
     size_t raw_cap = 0;

@@ -175,264 +175,6 @@ __device__ __forceinline__ int csad_count(int x, int y, int w, int h) {
     return nx * ny - 1;
 }
 
-template <int R, int DATA>
-__global__ void __launch_bounds__(256, 2) tv_iter_kernel(TvArgs a, int it) {
-    const int b = blockIdx.z;
-    if (!pair_active<DATA>(a, b, it)) return;
-
-    const int w = a.g.w, h = a.g.h, pitch = a.g.pitch;
-    const int lane = threadIdx.x;
-    const int x = (blockIdx.x * 32 + lane) * 4;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * R;
-    const bool xin = x < pitch;
-
-    const int par = (a.parity[b] + it) & 1;
-    const size_t B = a.g.B, plane = a.g.plane;
-    const float *in = a.state + (size_t)par * a.set_stride + (size_t)b * plane;
-    float *out = a.state + (size_t)(par ^ 1) * a.set_stride + (size_t)b * plane;
-    const size_t ks = B * plane;  // stride between state kinds
-    const float *cIx = a.Ix + (size_t)b * plane, *cIy = a.Iy + (size_t)b * plane;
-    const float tau = a.tau, l_t = a.l_t;
-
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto LD = [&](const float *base, int row) -> float4 {
-        return xin ? ld4(base + (size_t)row * pitch + x) : z4;
-    };
-
-    // ubar of the current row (+ right neighbour), carried down the march
-    float b1[5], b2[5];
-    {
-        const int yc = min(y0, h - 1);  // warps below the image only take part in the reduction
-        const float4 t1 = LD(in + ST_UB1 * ks, yc), t2 = LD(in + ST_UB2 * ks, yc);
-        b1[0] = t1.x, b1[1] = t1.y, b1[2] = t1.z, b1[3] = t1.w;
-        b2[0] = t2.x, b2[1] = t2.y, b2[2] = t2.z, b2[3] = t2.w;
-    }
-
-    // xi_new12 / xi_new22 of the row above the strip
-    float p12[4] = {0.f, 0.f, 0.f, 0.f}, p22[4] = {0.f, 0.f, 0.f, 0.f};
-    if (y0 > 0 && y0 < h) {
-        const int yu = y0 - 1;
-        const float4 q11 = LD(in + ST_XI11 * ks, yu), q12 = LD(in + ST_XI12 * ks, yu);
-        const float4 q21 = LD(in + ST_XI21 * ks, yu), q22 = LD(in + ST_XI22 * ks, yu);
-        const float4 c1 = LD(in + ST_UB1 * ks, yu), c2 = LD(in + ST_UB2 * ks, yu);
-        const float x11[4] = {q11.x, q11.y, q11.z, q11.w}, x12[4] = {q12.x, q12.y, q12.z, q12.w};
-        const float x21[4] = {q21.x, q21.y, q21.z, q21.w}, x22[4] = {q22.x, q22.y, q22.z, q22.w};
-        const float u1a[4] = {c1.x, c1.y, c1.z, c1.w}, u2a[4] = {c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float u1y = b1[k] - u1a[k], u2y = b2[k] - u2a[k];  // yu < h-1 always
-            p12[k] = x12[k] + tau * u1y;
-            p22[k] = x22[k] + tau * u2y;
-            if (DATA == DATA_TVL1) {
-                const float nrm = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
-                if (nrm > 1.f) {
-                    p12[k] /= nrm;
-                    p22[k] /= nrm;
-                }
-            } else {
-                const float n1 = proj_norm_hypot(x11[k], x12[k]);
-                const float n2 = proj_norm_hypot(x21[k], x22[k]);
-                if (n1 > 1.f) p12[k] /= n1;
-                if (n2 > 1.f) p22[k] /= n2;
-            }
-        }
-    }
-
-    float emax = 0.f;
-    double esum = 0.0;
-
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int y = y0 + r;
-        if (y >= h) break;  // warp-uniform (a warp shares y0)
-        const bool ylast = (y == h - 1);
-        // ---- loads of this row ----
-        const float4 q11 = LD(in + ST_XI11 * ks, y), q12 = LD(in + ST_XI12 * ks, y);
-        const float4 q21 = LD(in + ST_XI21 * ks, y), q22 = LD(in + ST_XI22 * ks, y);
-        const float4 qu1 = LD(in + ST_U1 * ks, y), qu2 = LD(in + ST_U2 * ks, y);
-        const float4 qix = LD(cIx, y), qiy = LD(cIy, y);
-        float4 qn1 = z4, qn2 = z4;
-        if (!ylast) {
-            qn1 = LD(in + ST_UB1 * ks, y + 1);
-            qn2 = LD(in + ST_UB2 * ks, y + 1);
-        }
-        float4 qrc = z4, qsc = z4;
-        if (DATA == DATA_TVL1)
-            qrc = LD(a.rho_c + (size_t)b * plane, y);
-        else
-            qsc = LD(a.scale + (size_t)b * plane, y);
-
-        // right neighbour of ubar: from the next lane, lane 31 loads it
-        b1[4] = __shfl_down_sync(0xffffffffu, b1[0], 1);
-        b2[4] = __shfl_down_sync(0xffffffffu, b2[0], 1);
-        if (lane == 31 && x + 4 < w) {
-            b1[4] = in[ST_UB1 * ks + (size_t)y * pitch + x + 4];
-            b2[4] = in[ST_UB2 * ks + (size_t)y * pitch + x + 4];
-        }
-
-        const float x11[4] = {q11.x, q11.y, q11.z, q11.w}, x12[4] = {q12.x, q12.y, q12.z, q12.w};
-        const float x21[4] = {q21.x, q21.y, q21.z, q21.w}, x22[4] = {q22.x, q22.y, q22.z, q22.w};
-        const float n1r[4] = {qn1.x, qn1.y, qn1.z, qn1.w}, n2r[4] = {qn2.x, qn2.y, qn2.z, qn2.w};
-        const float u1[4] = {qu1.x, qu1.y, qu1.z, qu1.w}, u2[4] = {qu2.x, qu2.y, qu2.z, qu2.w};
-        const float ix[4] = {qix.x, qix.y, qix.z, qix.w}, iy[4] = {qiy.x, qiy.y, qiy.z, qiy.w};
-        const float rc[4] = {qrc.x, qrc.y, qrc.z, qrc.w}, sc[4] = {qsc.x, qsc.y, qsc.z, qsc.w};
-
-        // ---- dual step: xi <- (xi + tau*grad(ubar)) / max(1, |xi_old|) ----
-        float m11[4], m12[4], m21[4], m22[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gx = x + k;
-            const float u1x = (gx < w - 1) ? b1[k + 1] - b1[k] : 0.f;
-            const float u2x = (gx < w - 1) ? b2[k + 1] - b2[k] : 0.f;
-            const float u1y = ylast ? 0.f : n1r[k] - b1[k];
-            const float u2y = ylast ? 0.f : n2r[k] - b2[k];
-            // x / max(1,|xi_old|): the divisor is exactly 1 wherever |xi_old| <= 1 (x/1 == x)
-            m11[k] = x11[k] + tau * u1x;
-            m12[k] = x12[k] + tau * u1y;
-            m21[k] = x21[k] + tau * u2x;
-            m22[k] = x22[k] + tau * u2y;
-            if (DATA == DATA_TVL1) {
-                const float nrm = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
-                if (nrm > 1.f) {
-                    m11[k] /= nrm;
-                    m12[k] /= nrm;
-                    m21[k] /= nrm;
-                    m22[k] /= nrm;
-                }
-            } else {
-                const float n1 = proj_norm_hypot(x11[k], x12[k]);
-                const float n2 = proj_norm_hypot(x21[k], x22[k]);
-                if (n1 > 1.f) {
-                    m11[k] /= n1;
-                    m12[k] /= n1;
-                }
-                if (n2 > 1.f) {
-                    m21[k] /= n2;
-                    m22[k] /= n2;
-                }
-            }
-        }
-
-        // xi_new11 / xi_new21 of the pixel to the left of this thread's quad
-        float l11 = __shfl_up_sync(0xffffffffu, m11[3], 1);
-        float l21 = __shfl_up_sync(0xffffffffu, m21[3], 1);
-        if (lane == 0 && x > 0) {
-            const size_t o = (size_t)y * pitch + x - 1;
-            const float e11 = in[ST_XI11 * ks + o], e12 = in[ST_XI12 * ks + o];
-            const float e21 = in[ST_XI21 * ks + o], e22 = in[ST_XI22 * ks + o];
-            const float c1 = in[ST_UB1 * ks + o], c2 = in[ST_UB2 * ks + o];
-            const float u1x = b1[0] - c1, u2x = b2[0] - c2;  // x-1 < w-1 always
-            l11 = e11 + tau * u1x;
-            l21 = e21 + tau * u2x;
-            if (DATA == DATA_TVL1) {
-                const float nrm = sqrtf(e11 * e11 + e12 * e12 + e21 * e21 + e22 * e22);
-                if (nrm > 1.f) {
-                    l11 /= nrm;
-                    l21 /= nrm;
-                }
-            } else {
-                const float n1 = proj_norm_hypot(e11, e12), n2 = proj_norm_hypot(e21, e22);
-                if (n1 > 1.f) l11 /= n1;
-                if (n2 > 1.f) l21 /= n2;
-            }
-        }
-
-        // ---- data term, primal step, extrapolation ----
-        float o1[4], o2[4], ob1[4], ob2[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gx = x + k;
-            const float d1 = div_bc(m11[k], k ? m11[k - 1] : l11, m12[k], p12[k], gx, y, w, h);
-            const float d2 = div_bc(m21[k], k ? m21[k - 1] : l21, m22[k], p22[k], gx, y, w, h);
-            float v1, v2;
-            if (DATA == DATA_TVL1) {
-                // thresholding operator TH (src/global_faldoi.cpp:693-717)
-                const float grad = ix[k] * ix[k] + iy[k] * iy[k];
-                const float rho = rc[k] + (ix[k] * u1[k] + iy[k] * u2[k]);
-                float e1, e2;
-                if (rho < -l_t * grad) {
-                    e1 = l_t * ix[k];
-                    e2 = l_t * iy[k];
-                } else if (rho > l_t * grad) {
-                    e1 = -l_t * ix[k];
-                    e2 = -l_t * iy[k];
-                } else if (grad_is_zero(grad)) {
-                    e1 = e2 = 0.f;
-                } else {
-                    const float fi = -rho / grad;
-                    e1 = fi * ix[k];
-                    e2 = fi * iy[k];
-                }
-                v1 = u1[k] + e1;
-                v2 = u2[k] + e2;
-            } else {
-                v1 = u1[k];
-                v2 = u2[k];
-                if (gx < w) {
-                    const float s = (ix[k] * u1[k] + iy[k] * u2[k]) / sc[k];
-                    const int np = csad_count(gx, y, w, h);
-                    const float med = csad_select(a.blk, a.sep, a.g, b, y, gx, np, s, l_t, sc[k]);
-                    v1 = csad_apply(u1[k], ix[k], med, sc[k]);
-                    v2 = csad_apply(u2[k], iy[k], med, sc[k]);
-                }
-            }
-            // primal step (ofTVl2_getP :325-335) and extrapolation (:780-783)
-            o1[k] = u1[k] - tau * (-d1 + div_const(u1[k] - v1, a.dth));
-            o2[k] = u2[k] - tau * (-d2 + div_const(u2[k] - v2, a.dth));
-            const float e = (o1[k] - u1[k]) * (o1[k] - u1[k]) + (o2[k] - u2[k]) * (o2[k] - u2[k]);
-            if (gx < w) {
-                emax = fmaxf(emax, e);
-                if (DATA == DATA_CSAD) esum += (double)e;
-            }
-            ob1[k] = 2 * o1[k] - u1[k];
-            ob2[k] = 2 * o2[k] - u2[k];
-        }
-
-        if (xin) {
-            const size_t o = (size_t)y * pitch + x;
-            st4(out + ST_XI11 * ks + o, make_float4(m11[0], m11[1], m11[2], m11[3]));
-            st4(out + ST_XI12 * ks + o, make_float4(m12[0], m12[1], m12[2], m12[3]));
-            st4(out + ST_XI21 * ks + o, make_float4(m21[0], m21[1], m21[2], m21[3]));
-            st4(out + ST_XI22 * ks + o, make_float4(m22[0], m22[1], m22[2], m22[3]));
-            st4(out + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
-            st4(out + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
-            st4(out + ST_UB1 * ks + o, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
-            st4(out + ST_UB2 * ks + o, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
-        }
-        // carry to the next row of the march
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            p12[k] = m12[k];
-            p22[k] = m22[k];
-            b1[k] = n1r[k];
-            b2[k] = n2r[k];
-        }
-    }
-
-    // ---- convergence measure: warp shuffle -> shared -> one atomic per CTA ----
-    __shared__ float red_max[8];
-    __shared__ double red_sum[8];
-    if (DATA == DATA_TVL1) {
-        emax = warp_max(emax);
-        if (lane == 0) red_max[threadIdx.y] = emax;
-    } else {
-        esum = warp_sum(esum);
-        if (lane == 0) red_sum[threadIdx.y] = esum;
-    }
-    __syncthreads();
-    if (threadIdx.y == 0 && lane == 0) {
-        if (DATA == DATA_TVL1) {
-            float m = red_max[0];
-            for (int i = 1; i < (int)blockDim.y; i++) m = fmaxf(m, red_max[i]);
-            atomicMax(a.err_max + (size_t)b * a.max_iters + it, __float_as_uint(m));
-        } else {
-            double t = red_sum[0];
-            for (int i = 1; i < (int)blockDim.y; i++) t += red_sum[i];
-            atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // CSAD per-warp constants (src/global_faldoi.cpp:1514-1534): scale =
 // hypot(Ix^2+Iy^2, 0.01) and, for the in-image neighbours j of the 7x7 window,

@@ -76,15 +76,20 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
     }
     if (!have_ihdr || w == 0 || h == 0) throw bad("no IHDR");
     if (interlace) throw bad("interlaced PNG is not supported");
+    // the header of an untrusted file: sizes that fit an int (and a sane pixel count), and only the bit depths
+    // the PNG specification allows for the colour type -- before any allocation or shift uses them
+    if (w > 0x7fffffffu || h > 0x7fffffffu || (uint64_t)w * h > (1ull << 30)) throw bad("image too large");
     int channels;
+    bool depth_ok;
     switch (ctype) {
-        case 0: channels = 1; break;
-        case 2: channels = 3; break;
-        case 3: channels = 1; break;
-        case 4: channels = 2; break;
-        case 6: channels = 4; break;
+        case 0: channels = 1, depth_ok = (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16); break;
+        case 2: channels = 3, depth_ok = (depth == 8 || depth == 16); break;
+        case 3: channels = 1, depth_ok = (depth == 1 || depth == 2 || depth == 4 || depth == 8); break;
+        case 4: channels = 2, depth_ok = (depth == 8 || depth == 16); break;
+        case 6: channels = 4, depth_ok = (depth == 8 || depth == 16); break;
         default: throw bad("unknown colour type");
     }
+    if (!depth_ok) throw bad("bit depth not allowed for this colour type");
     const size_t bpp_bits = (size_t)channels * depth;
     const size_t stride = (w * bpp_bits + 7) / 8;
     const size_t bpp = (bpp_bits + 7) / 8;  // filter unit in bytes
@@ -282,6 +287,8 @@ void write_flo(const std::string &path, const float *u1, const float *u2, int w,
         }
         f.write((const char *)row.data(), row.size() * sizeof(float));
     }
+    f.close();  // a full disk or an I/O error must not leave a truncated flow behind a successful exit
+    if (!f) throw std::runtime_error("error while writing '" + path + "'");
 }
 
 void write_image_float_split(const std::string &path, const float *planes, int w, int h, int pd) {
@@ -313,6 +320,8 @@ void write_png_gray8(const std::string &path, const int *values, int w, int h) {
     put_chunk(f, "IHDR", ihdr);
     put_chunk(f, "IDAT", comp);
     put_chunk(f, "IEND", {});
+    f.close();
+    if (!f) throw std::runtime_error("error while writing '" + path + "'");
 }
 
 }  // namespace faldoi_host

@@ -13,6 +13,8 @@
 #ifndef FALDOI_GPU_H
 #define FALDOI_GPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -88,6 +90,13 @@ void faldoi_solver_destroy(faldoi_solver *s);
 int faldoi_solver_upload(faldoi_solver *s, int slot, const float *I0, const float *I1, const float *Im1,
                          const float *lab, const float *u, const float *chi);
 
+/* TV family (methods 0,1,4,5): the caller's dual variables xi11..xi22 (w*h each) as the initial duals of `slot`
+ * (call after faldoi_solver_upload, which zeroes them), and the final duals after a run -- what the reference's
+ * tvl2OF / tvcsad_PD read and update in place through their xi arguments (src/global_faldoi.cpp:556-573). */
+int faldoi_solver_upload_xi(faldoi_solver *s, int slot, const float *xi11, const float *xi12, const float *xi21,
+                            const float *xi22);
+int faldoi_solver_download_xi(faldoi_solver *s, int slot, float *xi11, float *xi12, float *xi21, float *xi22);
+
 /* Same, but from the RAW frames as iio_read_image_float_split returns them (planar, pd
  * channels, dense w*h per plane, 0..255): main()'s preprocessing -- rgb2gray, the joint
  * normalisation, gaussian(0.9) and, for the NLTV methods, image_to_lab
@@ -110,6 +119,12 @@ int faldoi_solver_sync(faldoi_solver *s);
  * occlusion mask chi in {0,1} (w*h); log may be NULL. */
 int faldoi_solver_download(faldoi_solver *s, int slot, float *u, float *chi, faldoi_log *log);
 
+/* NLTV models only (methods 2,3,6,7).  The default arithmetic is the reference's own -- IEEE divisions, ascending
+ * slot order -- and gives bit-identical flows.  fast != 0 opts this handle into approximate divisions
+ * (MUFU.RCP + FMUL, 2 ulp) and a paired slot order: about 1.7x the throughput, mean |du| ~ 1e-6 px, but the CSAD
+ * variants are chaotic enough that a few pixels of a full-size frame can exceed the 1e-2 px maximum. */
+int faldoi_solver_set_nltv_fast(faldoi_solver *s, int fast);
+
 /* Milliseconds the last faldoi_solver_run spent on the device (CUDA events on the handle's stream). */
 float faldoi_solver_last_run_ms(faldoi_solver *s);
 /* Of that, the milliseconds between the first and last per-iteration launch of every warp
@@ -122,9 +137,16 @@ void *faldoi_solver_stream(faldoi_solver *s);
 /* Device pointer to the flow of pair `slot` (2 planes of h rows with the given pitch in floats). */
 float *faldoi_solver_device_flow(faldoi_solver *s, int slot, int *pitch_floats);
 
+/* Page-locked host memory for staging buffers (copies from / to it are asynchronous and run at full PCIe rate);
+ * usable with every entry point that takes host pointers.  NULL on failure. */
+void *faldoi_pinned_alloc(size_t bytes);
+void faldoi_pinned_free(void *p);
+
 /* ---- one-call host entry: H2D, solve, D2H ----------------------------------
  * The single call the host `global_faldoi` makes after preprocessing
- * (replaces src/global_faldoi.cpp:2132-2167).  u (and chi) are updated in place. */
+ * (replaces src/global_faldoi.cpp:2132-2167).  u (and chi) are updated in place.
+ * Re-entrant: the single-pair handle behind it is cached per host thread (and device, size, method), so one
+ * host thread per GPU can drive 8 GPUs concurrently. */
 int faldoi_global_solve(int device, const faldoi_params *p, int w, int h, const float *I0, const float *I1,
                         const float *Im1, const float *lab, float *u, float *chi, faldoi_log *log);
 
@@ -134,8 +156,9 @@ int faldoi_global_solve_raw(int device, const faldoi_params *p, int w, int h, in
                             const float *im1, float *u, float *chi, faldoi_log *log);
 
 /* ---- per-solver mirrors of the reference's in-process signatures -----------
- * Same argument order and in-place semantics as the reference functions; the
- * only addition is the int status.  `verbose` prints the reference's per-warp
+ * Same argument order and in-place semantics as the reference functions (u1,u2 AND the xi arrays of tvl2OF /
+ * tvcsad_PD are read as the initial state and hold the final state on return; xi pointers may be NULL = start
+ * from zero); the only addition is the int status.  `verbose` prints the reference's per-warp
  * line to stderr (methods 0,4) / stdout (methods 2,6).
  *   tvl2OF       src/global_faldoi.cpp:556-573
  *   tvcsad_PD    src/global_faldoi.cpp:1449-1466

@@ -50,6 +50,34 @@ def test_ragged_sizes_vs_oracle(fb, po, w, h, method):
     assert_flow(u, ou, exact=True)
 
 
+@pytest.mark.parametrize("w,h", [(300, 131), (257, 9), (130, 67), (129, 5)])
+@pytest.mark.parametrize("method", [2, 6, 8])
+def test_ragged_sizes_vs_oracle_other_models(fb, po, w, h, method):
+    """The NLTV / NLTV-CSAD / TVL2-OCC tile kernels on frames wider than one and two tiles (NLTV tiles are 128
+    wide, OCC tiles 120) and not a multiple of anything: bit-exact against the oracle, chi included."""
+    I0, I1, Im1, u0, rgb = synthetic_pair(w, h, seed=3 * w + h + method)
+    lab = po.o_image_to_lab(rgb) if method in (2, 6) else None
+    chi0 = (np.random.default_rng(w + h).random((h, w)) > 0.85).astype(np.float32) if method == 8 else None
+    warps, iters = (1, 400) if method != 8 else (2, 8)
+    u, chi, its, _ = fb.global_solve(method, I0, I1, u0, Im1=Im1 if method == 8 else None, lab=lab, chi=chi0, warps=warps,
+                                     glb_iters=iters)
+    ou, ochi, oits, _ = po.o_global_solve(method, I0, I1, Im1, lab, u0, chi0, warps=warps, glb_iters=iters)
+    assert its == oits
+    assert_flow(u, ou, exact=True)
+    if method == 8:
+        assert np.array_equal(chi, ochi)
+
+
+def test_4k_tvl2_vs_oracle(fb, po):
+    """BASELINE configs[4]'s large shape: one 3840x2160 TVL2 warp against the oracle on the host cores (the frame
+    is 32 x 240 tiles of the two-iteration kernel; 41 planes of 33 MB are far beyond L2)."""
+    I0, I1, _, u0, _ = synthetic_pair(3840, 2160, seed=4)
+    u, _, its, errs = fb.global_solve(0, I0, I1, u0, warps=1)
+    ou, _, oits, oerrs = po.o_global_solve(0, I0, I1, None, None, u0, warps=1)
+    assert its == oits and errs == oerrs
+    assert np.array_equal(u, ou)
+
+
 def test_batch_equals_single(fb, po):
     """Pairs of one batch are independent problems with their own exit iteration."""
     w, h, B = 96, 64, 5
@@ -87,6 +115,42 @@ def test_reference_signature_mirrors(fb, po):
     u1, u2, chi = g["u0"][0].copy(), g["u0"][1].copy(), g["chi0"].copy()
     fb.guided_tvl2coupled_occ(g["I0n"], g["I1n"], g["Im1n"], u1, u2, chi, fb.default_params(8, 12, 1), w, h)
     assert np.array_equal(np.stack([u1, u2]), g["u_m8_w1_i12"]) and np.array_equal(chi, g["chi_m8_w1_i12"])
+
+
+def test_mirrors_read_and_return_the_duals(fb, po):
+    """tvl2OF's xi arguments are in/out (src/global_faldoi.cpp:556-573): two 1-warp calls that hand the duals over
+    must equal one 2-warp call (the reference carries xi across warps), and the returned duals equal the oracle's."""
+    g = load_case("crop_b")
+    h, w = g["I0n"].shape
+    u1, u2 = g["u0"][0].copy(), g["u0"][1].copy()
+    xi = [np.zeros((h, w), np.float32) for _ in range(4)]
+    for _ in range(2):
+        fb.tvl2OF(g["I0n"], g["I1n"].copy(), u1, u2, *xi, 40.0, 0.3, 0.125, 0.01, w, h, 1, 0)
+    ou, oxi, _, _ = po.o_tvl2(g["I0n"], g["I1n"], g["u0"], warps=2)
+    assert np.array_equal(np.stack([u1, u2]), ou)
+    assert np.array_equal(np.stack(xi), oxi)
+    assert any(np.abs(x).max() > 0 for x in xi)
+
+
+def test_nltv_second_run_continues_from_the_first(fb, po):
+    """A second faldoi_solver_run on an NLTV handle without a fresh upload continues from the state the first one
+    left (odd warps*max_iters leaves it in the other ping-pong set): 1 + 1 warps of 3 iterations == 2 warps."""
+    g = load_case("crop_b")
+    h, w = g["I0n"].shape
+    p = fb.default_params(2, warps=1)
+    p.max_iters = 3
+    s = fb.Solver(w, h, 2, 1)
+    s.upload(0, g["I0n"], g["I1n"], g["u0"], lab=g["lab"])
+    s.run(p)
+    s.run(p)
+    u, _, _ = s.download(0)
+    p2 = fb.default_params(2, warps=2)
+    p2.max_iters = 3
+    s.upload(0, g["I0n"], g["I1n"], g["u0"], lab=g["lab"])
+    s.run(p2)
+    u2, _, _ = s.download(0)
+    s.close()
+    assert np.array_equal(u, u2)
 
 
 def test_primitives(fb, po):
@@ -276,14 +340,19 @@ def test_fullsize_reference_pair_other_models(fb, po, method):
 
 
 @pytest.mark.parametrize("method", [2, 6])
-def test_nltv_fast_mode_within_tolerance(fb, po, method, monkeypatch):
-    """FALDOI_NLTV_FAST=1: approximate divisions and paired slot order, the opt-in throughput mode of the NLTV
-    models -- held to the north star's tolerance on the goldens (the default mode is bit-exact, test_golden)."""
-    monkeypatch.setenv("FALDOI_NLTV_FAST", "1")
+def test_nltv_fast_mode_within_tolerance(fb, po, method):
+    """faldoi_solver_set_nltv_fast: approximate divisions and paired slot order, the opt-in throughput mode of the
+    NLTV models -- held to the north star's tolerance on the goldens (the default mode is bit-exact, test_golden)."""
     for case in ("crop_a", "crop_b"):
         g = load_case(case)
         run = [r for r in CASE_RUNS[case] if r[0] == method][0]
-        u, _, its, _ = fb.global_solve(method, g["I0n"], g["I1n"], g["u0"], Im1=g["Im1n"], lab=g["lab"], warps=run[1], glb_iters=run[2])
+        h, w = g["I0n"].shape
+        s = fb.Solver(w, h, method, 1)
+        s.set_nltv_fast(True)
+        s.upload(0, g["I0n"], g["I1n"], g["u0"], lab=g["lab"])
+        s.run(fb.default_params(method, run[2], run[1]))
+        u, _, _ = s.download(0)
+        s.close()
         ref = g["u_" + run_key(*run)]
         assert not np.array_equal(u, ref), "fast mode did not take effect"
         assert_flow(u, ref, exact=False)

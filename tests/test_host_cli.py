@@ -284,6 +284,42 @@ def test_cli_sequence_mode(H, tmp_path, po):
 
 
 @pytest.mark.gpu
+def test_cli_sequence_batched_mixed_sizes(H, tmp_path, po):
+    """-seq fills the slots of a batched handle with consecutive jobs of equal size (-batch 2 here: batches of 2, 1, 2, 1
+    as the size changes), through pinned staging; every result equals the single-call result.  -devices all shards
+    the batches over every visible GPU."""
+    ga, gb = load_case("crop_a"), load_case("crop_b")
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    ims_a, flo_a = _write_case(tmp_path / "a", ga, po)
+    ims_b, flo_b = _write_case(tmp_path / "b", gb, po)
+    order = "aaabbb"
+    outs = [str(tmp_path / ("o%d.flo" % k)) for k in range(len(order))]
+    (tmp_path / "jobs.txt").write_text("".join("%s %s %s\n" % ((ims_a, flo_a, o) if c == "a" else (ims_b, flo_b, o))
+                                               for c, o in zip(order, outs)))
+    for extra in ([], ["-devices", "all"]):
+        r = subprocess.run([BIN, "-seq", str(tmp_path / "jobs.txt"), "-m", "0", "-w", "3", "-batch", "2", "-verbose", "1"] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "sequence: 6 pairs done" in r.stderr
+        ua, _, ia, _ = po.o_global_solve(0, ga["I0n"], ga["I1n"], None, None, ga["u0"], warps=3)
+        for c, o in zip(order, outs):
+            assert np.array_equal(po.read_flo(o), ua if c == "a" else gb["u_m0_w3"])
+            os.remove(o)
+        assert r.stderr.count("Warping: 0,Iter:") == 6
+
+
+def test_cli_unknown_method_writes_input_flow(H, tmp_path, po):
+    """Method ids outside 0..8: the reference's dispatch matches nothing and main() saves the input flow unchanged."""
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po)
+    out = str(tmp_path / "out.flo")
+    r = subprocess.run([BIN, ims, flo, out, "-m", "-1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(flo, "rb").read()
+
+
+@pytest.mark.gpu
 def test_cli_sequence_pipeline_occ_and_errors(H, tmp_path, po):
     """-seq with method 8 (flow + occlusion PNG per job, written by the background writer) and a job whose
     input is missing: the run stops with a non-zero code, the jobs before it are complete on disk."""

@@ -84,6 +84,24 @@ def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n, sync, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_striped_4k_equals_whole_frame(fb):
+    """The shape the stripes exist for: a 3840x2160 pair in 3 stripes (device 0, or one per GPU when there are
+    several) against the whole-frame solve, one warp."""
+    w, h = 3840, 2160
+    I0, I1, _, u0, _ = synthetic_pair(w, h, seed=9)
+    p = fb.default_params(0, warps=1)
+    whole, _, its, errs = fb.global_solve(0, I0, I1, u0, params=p)
+    ndev = fb.device_count()
+    g = fb.Stripes(w, h, [k % ndev for k in range(3)])
+    g.upload(I0, I1, u0)
+    g.run(p)
+    u, log = g.download()
+    assert list(log.iters[:1]) == its and list(log.err[:1]) == errs
+    assert np.array_equal(u, whole)
+    g.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("sync", ["events", "memops"])
 def test_striped_across_gpus(fb, sync, monkeypatch):
     """With >= 2 GPUs: one stripe per GPU, NVLink peer stores."""
