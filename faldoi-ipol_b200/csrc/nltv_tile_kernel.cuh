@@ -33,9 +33,12 @@ namespace faldoi {
 #ifndef FALDOI_NLT_CTAS
 #define FALDOI_NLT_CTAS 3
 #endif
+#ifndef FALDOI_NLT_H
+#define FALDOI_NLT_H 8  // tile rows = warps per CTA
+#endif
 enum {
     NLT_W = 128,
-    NLT_H = 8,
+    NLT_H = FALDOI_NLT_H,
     NLT_PW = NLT_W + 8,   // apron tile: cols x0-4 .. x0+131
     NLT_AR = NLT_H + 4,   // apron tile: rows y0-2 .. y0+NLT_H+1
     NLT_THREADS = 32 * NLT_H,
@@ -105,6 +108,22 @@ __device__ __forceinline__ void nl_shifted4(const float *row, int l, float (&out
 #pragma unroll
         for (int i = 0; i < 4; i++) out[i] = t[i + l];
     }
+}
+
+// wt (a sum of up to 24 weights in (0, 1]) inside the divisor range of the reciprocal-based quotients
+__device__ __forceinline__ bool nl_wt_ok(float wt) { return wt >= 0.0009765625f && wt < 1048576.f; }  // [2^-10, 2^20)
+// weighted flow difference t = w*(ubar_p - ubar_q): zero or 2^-50 <= |t| <= 2^10
+__device__ __forceinline__ bool nl_num_ok(float t) {
+    const float a = fabsf(t);
+    return a == 0.f || (a >= 8.881784197001252e-16f && a <= 1024.f);
+}
+
+// the dual update of one pixel and slot with plain IEEE divisions (operands outside the range test of the fast path)
+__device__ __noinline__ float4 nl_slot_update_ieee(float t1, float t2, float wp, float wq, float po, float qo, float pr, float qr, float tau) {
+    const float g1 = t1 / wp, g2 = t2 / wp;
+    const float h1 = -t1 / wq, h2 = -t2 / wq;
+    return make_float4((po + tau * g1) / (1 + tau * fabsf(g1)), (qo + tau * g2) / (1 + tau * fabsf(g2)),
+                       (pr + tau * h1) / (1 + tau * fabsf(h1)), (qr + tau * h2) / (1 + tau * fabsf(h2)));
 }
 
 template <int DATA, bool EXACT>
@@ -212,6 +231,17 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
         for (int i = 0; i < 4; i++) rwp[i] = rwp[i] > 0.f ? rwp[i] : 1.f;
     }
     float dP[4] = {0.f, 0.f, 0.f, 0.f}, dQ[4] = {0.f, 0.f, 0.f, 0.f};
+    // exact mode: wt of the own pixel divides 48 quotients per iteration -- its refined reciprocal (the one IEEE
+    // division's own fast path computes) is formed once; okp = wt is in the range where that path is exact
+    float rcp_p[4] = {1.f, 1.f, 1.f, 1.f};
+    bool okp[4] = {false, false, false, false};
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            okp[i] = nl_wt_ok(rwp[i]);
+            rcp_p[i] = rcp_refined(okp[i] ? rwp[i] : 1.f);
+        }
+    }
 
     // ---- the 24 slots: dual update + non-local divergence ----
     // The slot loop is rolled over the window rows (5 bodies instead of 24: the fully unrolled exact
@@ -245,28 +275,38 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
                 const float t1 = wm * (c1[i] - q1), t2 = wm * (c2[i] - q2);
                 float Pr, Qr;
                 if (EXACT) {
-                    // the reference's operations, one for one (ofnltv_getD :1127-1174): (w*(u_p-u_q))/wt, then
-                    // (sc + tau*g)/(1 + tau*sqrt(g*g)); sqrt(g*g) == |g| whenever g*g is a normal float, and
-                    // below that 1 + tau*(either) rounds to 1.  A slot without neighbour divides by 1, not by
-                    // the zero fill.
-                    if (t1 == 0.f && t2 == 0.f) {
-                        // Slots without a neighbour (weight clamped to 0), the pitch padding and flat regions:
-                        // g = 0/wt = 0 with the sign of t, and the update divides by exactly 1.  Same bits as the
-                        // general branch, but these lanes stay out of it: IEEE division sends zero numerators to
-                        // its out-of-line slow path, and one such lane drags the whole warp along (14 % of the
-                        // kernel's instructions before this test).
-                        pn[i] = po[i] + tau * t1;
-                        qn[i] = qo[i] + tau * t2;
-                        Pr = pr[i] + tau * -t1;
-                        Qr = qr[i] + tau * -t2;
-                    } else {
-                        const float wq = wm > 0.f ? nrw[i] : 1.f;
-                        const float g1 = t1 / rwp[i], g2 = t2 / rwp[i];
-                        pn[i] = (po[i] + tau * g1) / (1 + tau * fabsf(g1));
-                        qn[i] = (qo[i] + tau * g2) / (1 + tau * fabsf(g2));
-                        const float h1 = -t1 / wq, h2 = -t2 / wq;
-                        Pr = (pr[i] + tau * h1) / (1 + tau * fabsf(h1));
-                        Qr = (qr[i] + tau * h2) / (1 + tau * fabsf(h2));
+                    // The reference's operations, one for one (ofnltv_getD :1127-1174): g = (w*(u_p-u_q))/wt, then
+                    // (sc + tau*g)/(1 + tau*sqrt(g*g)); sqrt(g*g) == |g| whenever g*g is a normal float, and below
+                    // that 1 + tau*(either) rounds to 1.  A slot without neighbour divides by 1, not by the zero fill.
+                    //
+                    // All eight quotients take the instruction sequence of IEEE division's own fast path without its
+                    // per-division range check and slow-path call (common.cuh: rcp_refined + div_by_rcp; the two
+                    // quotients by the own wt and the two by the neighbour's share a reciprocal).  One range test per
+                    // pixel and slot stands in for the eight checks:
+                    //   * wt, wt_q in [2^-10, 2^20) and |t| = 0 or in [2^-50, 2^10]  =>  |g|, |h| = 0 or in [2^-70, 2^20]:
+                    //     every divisor 1 + tau*|g| is a normal number in [1, 2^21) and no intermediate of the
+                    //     first four quotients leaves the normal range;
+                    //   * the numerators sc + tau*g: |sc| <= 1 (the update maps [-1,1] into itself), so they are below
+                    //     2^21, and a non-zero sum of two floats is at least half an ulp of the smaller-magnitude one,
+                    //     i.e. >= 2^-97 here, or it is exactly +0 (round to nearest), which the sequence maps to +0 as
+                    //     division does.  A dual never becomes -0 (induction from the +0 start), so zero numerators
+                    //     of slots without neighbour, of the padding and of flat regions are exact as well -- and,
+                    //     unlike IEEE division, this path has no slow branch for them to drag their warp into.
+                    // Anything outside the test takes plain IEEE division.
+                    const float wq = wm > 0.f ? nrw[i] : 1.f;
+                    const bool fast_ok = okp[i] && nl_wt_ok(wq) && nl_num_ok(t1) && nl_num_ok(t2);
+                    if (fast_ok) {
+                        const float rq = rcp_refined(wq);
+                        const float g1 = div_by_rcp(t1, rwp[i], rcp_p[i]), g2 = div_by_rcp(t2, rwp[i], rcp_p[i]);
+                        const float h1 = div_by_rcp(-t1, wq, rq), h2 = div_by_rcp(-t2, wq, rq);
+                        const float d1 = 1 + tau * fabsf(g1), d2 = 1 + tau * fabsf(g2), e1 = 1 + tau * fabsf(h1), e2 = 1 + tau * fabsf(h2);
+                        pn[i] = div_by_rcp(po[i] + tau * g1, d1, rcp_refined(d1));
+                        qn[i] = div_by_rcp(qo[i] + tau * g2, d2, rcp_refined(d2));
+                        Pr = div_by_rcp(pr[i] + tau * h1, e1, rcp_refined(e1));
+                        Qr = div_by_rcp(qr[i] + tau * h2, e2, rcp_refined(e2));
+                    } else {  // out of line: keeps eight IEEE divisions per pixel and slot out of the hot loop's code
+                        const float4 r4 = nl_slot_update_ieee(t1, t2, rwp[i], wq, po[i], qo[i], pr[i], qr[i], tau);
+                        pn[i] = r4.x, qn[i] = r4.y, Pr = r4.z, Qr = r4.w;
                     }
                 } else {
                     const float rwq = nrw[i];

@@ -12,6 +12,7 @@
 //                    (w*h >= 3840*2160, TVL2) is cut into row stripes over them (halo rows exchanged over NVLink);
 //                    a sequence is sharded by pair, one host thread + batched handle per GPU
 //   -stripes 0       never cut a frame into stripes
+//   -seq_stats 1     per GPU, where the host thread of a sequence spent its time (stderr)
 //   -host_preproc 1  run main()'s preprocessing on the host instead of the GPU
 //   -seq jobs.txt    many pairs in one process (one job per line: the positional arguments of a normal call).
 //                    Files are read and decoded by a pool of host threads, jobs of equal size fill the slots of a
@@ -19,6 +20,8 @@
 //                    written by background threads -- SURVEY 8f rows 3 and 4; what the reference's scripts do with
 //                    one process per pair (scripts_python/faldoi_sift.py:314-318)
 // There is no CPU fallback: without a usable GPU the program reports the error and fails.
+#include <malloc.h>
+
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -28,6 +31,7 @@
 #include <ctime>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <future>
 #include <iostream>
 #include <memory>
@@ -96,10 +100,18 @@ bool is_nltv(int m) {
 
 struct Options {
     int val_method = 0, nwarps = 5, glb_it = 400, device = 0, batch = 16;
-    bool verbose = false, host_preproc = false, stripes = true;
+    bool verbose = false, host_preproc = false, stripes = true, seq_stats = false;
     std::vector<int> devices;
     std::string file_params;
 };
+
+// Page-locked staging memory of one job in flight (sequence mode): the loaders decode the frames, the flow and the
+// occlusion mask straight into it, the GPU copies from and back into it, the writers save from it.
+struct Slot {
+    float *pin = nullptr;
+    size_t cap = 0;  // floats
+};
+bool g_pinned_staging = true;  // false when no CUDA device is visible (page-locking needs the driver)
 
 // Stage 1 of a job (host I/O, no messages): ims.txt + the frames, the flow and the occlusion
 // mask.  A single call decodes its files concurrently; a sequence decodes many jobs at once
@@ -110,7 +122,7 @@ struct Loaded {
     std::exception_ptr err;
 };
 
-Loaded load_inputs(const std::vector<std::string> &args, int val_method, bool parallel) {
+Loaded load_inputs(const std::vector<std::string> &args, int val_method, bool parallel, Slot *slot = nullptr) {
     Loaded L;
     try {
         // ims.txt: line 1 = I0, line 2 = I1, line 3 = I-1, line 4 = I2 (unused)
@@ -126,13 +138,34 @@ Loaded load_inputs(const std::vector<std::string> &args, int val_method, bool pa
         }
         // with fewer than 4 lines the reference reads I1 in place of I-1 (:1933-1937)
         const std::string third = (L.num_files == 4) ? filename_i_1 : filename_i1;
-        auto rd = [](std::string f) { return faldoi_host::read_image_split(f); };
+        const bool third_is_i1 = (third == filename_i1);  // the same file: decode it once
+        // staging layout from the first frame's header: three frames of pd planes, the flow (2), the mask (1)
+        faldoi_host::Sink s0, s1, s2, sf, so;
+        if (slot && g_pinned_staging) {
+            try {
+                int w = 0, h = 0, pd = 0;
+                faldoi_host::probe_image(filename_i0, &w, &h, &pd);
+                const size_t n = (size_t)w * h, need = (3 * (size_t)pd + 3) * n;
+                if (need > slot->cap) {
+                    faldoi_pinned_free(slot->pin);
+                    slot->pin = (float *)faldoi_pinned_alloc(need * sizeof(float));
+                    slot->cap = slot->pin ? need : 0;
+                }
+                if (slot->pin) {
+                    float *p = slot->pin;
+                    s0 = {p, pd * n}, s1 = {p + pd * n, pd * n}, s2 = {p + 2 * pd * n, pd * n};
+                    sf = {p + 3 * pd * n, 2 * n}, so = {p + 3 * pd * n + 2 * n, n};
+                }
+            } catch (...) {  // the real read below reports what is wrong with the file
+            }
+        }
+        auto rd = [](std::string f, faldoi_host::Sink s) { return faldoi_host::read_image_split(f, s); };
         const auto policy = parallel ? std::launch::async : std::launch::deferred;
-        std::future<Image> f0 = std::async(policy, rd, filename_i0);
-        std::future<Image> f1 = std::async(policy, rd, filename_i1);
-        std::future<Image> ff = std::async(policy, rd, args[2]);
+        std::future<Image> f0 = std::async(policy, rd, filename_i0, s0);
+        std::future<Image> f1 = std::async(policy, rd, filename_i1, s1);
+        std::future<Image> ff = std::async(policy, rd, args[2], sf);
         std::future<Image> fo;
-        if (val_method >= 8) fo = std::async(policy, rd, args.size() == 6 ? args[4] : std::string());
+        if (val_method >= 8) fo = std::async(policy, rd, args.size() == 6 ? args[4] : std::string(), so);
         std::exception_ptr first;
         auto take = [&](std::future<Image> &f, Image &dst) {
             try {
@@ -141,9 +174,8 @@ Loaded load_inputs(const std::vector<std::string> &args, int val_method, bool pa
                 if (!first) first = std::current_exception();
             }
         };
-        const bool third_is_i1 = (third == filename_i1);  // the same file: decode it once
         try {  // same order as the reference reads them, so the same file is blamed first
-            if (!third_is_i1) L.i_1 = rd(third);
+            if (!third_is_i1) L.i_1 = rd(third, s2);
         } catch (...) {
             first = std::current_exception();
         }
@@ -165,7 +197,8 @@ struct Ready {
     int method = 0, w = 0, h = 0, pd = 0;
     bool passthrough = false;  // method id outside 0..8: the reference writes the input flow back unchanged
     faldoi_params params{};
-    std::vector<float> u, chi;
+    float *u = nullptr, *chi = nullptr;  // flow (u1 | u2) and occlusion mask, in and out: the decoded images' storage
+    int slot = -1;                       // staging slot to give back once the results are on disk (sequence mode)
     std::string flow_file, occ_file;
     faldoi_log log{};
     double secs = 0;
@@ -231,8 +264,9 @@ int prepare_job(const std::vector<std::string> &args, const Options &opt, Loaded
         fprintf(stderr, "GaussianSmooth: sigma too large\n");
         return EXIT_FAILURE;
     }
-    R.u = std::move(R.in.flow.data);  // u1 | u2
-    if (val_method >= 8 && !R.passthrough) R.chi.assign(occ.data.begin(), occ.data.begin() + size);
+    (void)size;
+    R.u = R.in.flow.px();  // u1 | u2
+    if (val_method >= 8 && !R.passthrough) R.chi = R.in.occ.px();
     if (val_method == FALDOI_M_NLTVL1 || val_method == FALDOI_M_NLTVL1_W) std::printf("Before\nInitialization\n");
     return EXIT_SUCCESS;
 }
@@ -256,7 +290,7 @@ void report_job(const Ready &R, bool verbose) {
 
 // Stage 3 of a job: the output files.
 void save_job(const Ready &R) {
-    faldoi_host::write_image_float_split(R.flow_file, R.u.data(), R.w, R.h, 2);
+    faldoi_host::write_image_float_split(R.flow_file, R.u, R.w, R.h, 2);
     if (R.method == FALDOI_M_TVL1_OCC && !R.passthrough) {
         std::vector<int> occ((size_t)R.w * R.h);
         for (size_t i = 0; i < occ.size(); i++) occ[i] = (int)R.chi[i];
@@ -274,10 +308,9 @@ HostFrames host_preprocess(const Ready &R) {
     F.i0n.resize(size), F.i1n.resize(size), F.i_1n.resize(size);
     if (is_nltv(R.method)) {
         F.lab.resize(3 * size);
-        faldoi_host::image_to_lab(R.in.i0.data.data(), (int)size, F.lab.data());
+        faldoi_host::image_to_lab(R.in.i0.px(), (int)size, F.lab.data());
     }
-    faldoi_host::preprocess(R.in.i0.data.data(), R.in.i1.data.data(), R.in.i_1.data.data(), R.pd, R.w, R.h, F.i0n.data(), F.i1n.data(),
-                            F.i_1n.data());
+    faldoi_host::preprocess(R.in.i0.px(), R.in.i1.px(), R.in.i_1.px(), R.pd, R.w, R.h, F.i0n.data(), F.i1n.data(), F.i_1n.data());
     return F;
 }
 
@@ -297,36 +330,125 @@ int solve_single(Ready &R, const Options &opt) {
         const HostFrames F = host_preprocess(R);
         faldoi_stripes *g = nullptr;
         rc = faldoi_stripes_create(&g, (int)opt.devices.size(), opt.devices.data(), R.w, R.h, R.method);
-        if (rc == FALDOI_OK) rc = faldoi_stripes_upload(g, F.i0n.data(), F.i1n.data(), R.u.data());
+        if (rc == FALDOI_OK) rc = faldoi_stripes_upload(g, F.i0n.data(), F.i1n.data(), R.u);
         if (rc == FALDOI_OK) rc = faldoi_stripes_run(g, &R.params);
-        if (rc == FALDOI_OK) rc = faldoi_stripes_download(g, R.u.data(), &R.log);
+        if (rc == FALDOI_OK) rc = faldoi_stripes_download(g, R.u, &R.log);
         faldoi_stripes_destroy(g);
         if (rc == FALDOI_OK) fprintf(stderr, "row stripes: %d GPUs\n", (int)opt.devices.size());
     } else if (opt.host_preproc) {
         const HostFrames F = host_preprocess(R);
         rc = faldoi_global_solve(opt.device, &R.params, R.w, R.h, F.i0n.data(), F.i1n.data(), F.i_1n.data(), is_nltv(R.method) ? F.lab.data() : nullptr,
-                                 R.u.data(), R.method >= 8 ? R.chi.data() : nullptr, &R.log);
+                                 R.u, R.method >= 8 ? R.chi : nullptr, &R.log);
     } else {
-        rc = faldoi_global_solve_raw(opt.device, &R.params, R.w, R.h, R.pd, R.in.i0.data.data(), R.in.i1.data.data(), R.in.i_1.data.data(),
-                                     R.u.data(), R.method >= 8 ? R.chi.data() : nullptr, &R.log);
+        rc = faldoi_global_solve_raw(opt.device, &R.params, R.w, R.h, R.pd, R.in.i0.px(), R.in.i1.px(), R.in.i_1.px(), R.u,
+                                     R.method >= 8 ? R.chi : nullptr, &R.log);
     }
     R.secs = std::chrono::duration<double>(std::chrono::system_clock::now() - t0).count();
     return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Sequence mode: loaders -> dispatcher (job order, main()'s checks) -> one worker per GPU (batches) -> writers
+// Sequence mode: loaders -> dispatcher (job order, main()'s checks) -> one worker per GPU (batches) -> writers.
+// Every job in flight owns a page-locked staging slot from the moment its files are decoded until its results
+// are on disk; loaders and writers are persistent pool threads (their scratch buffers are reused from job to job).
 // ---------------------------------------------------------------------------------------------------------------
+class ThreadPool {
+  public:
+    explicit ThreadPool(size_t n) {
+        for (size_t i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~ThreadPool() {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    template <class F>
+    auto submit(F f) -> std::future<decltype(f())> {
+        auto task = std::make_shared<std::packaged_task<decltype(f())()>>(std::move(f));
+        auto fut = task->get_future();
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            q_.push_back([task] { (*task)(); });
+        }
+        cv_.notify_one();
+        return fut;
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [this] { return quit_ || !q_.empty(); });
+                if (q_.empty()) return;
+                job = std::move(q_.front());
+                q_.pop_front();
+            }
+            job();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::deque<std::function<void()>> q_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool quit_ = false;
+};
+
+class SlotPool {
+  public:
+    explicit SlotPool(size_t n) : slots_(n) {
+        for (size_t i = 0; i < n; i++) free_.push_back((int)i);
+    }
+    ~SlotPool() {
+        for (Slot &s : slots_) faldoi_pinned_free(s.pin);
+    }
+    int try_acquire() {
+        std::lock_guard<std::mutex> l(mu_);
+        if (free_.empty()) return -1;
+        const int id = free_.back();
+        free_.pop_back();
+        return id;
+    }
+    int acquire() {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [this] { return !free_.empty(); });
+        const int id = free_.back();
+        free_.pop_back();
+        return id;
+    }
+    void release(int id) {
+        if (id < 0) return;
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            free_.push_back(id);
+        }
+        cv_.notify_one();
+    }
+    Slot *at(int id) { return &slots_[id]; }
+
+  private:
+    std::vector<Slot> slots_;
+    std::vector<int> free_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+};
+
 struct Batch {
     std::vector<std::unique_ptr<Ready>> jobs;
 };
 
-// One GPU: a host thread, a batched solver handle and pinned staging for its slots.
+// One GPU: a host thread and a batched solver handle.
 class DeviceWorker {
   public:
-    DeviceWorker(int device, const Options &opt) : device_(device), opt_(opt) { th_ = std::thread([this] { loop(); }); }
+    DeviceWorker(int device, const Options &opt, ThreadPool &io, SlotPool &slots) : device_(device), opt_(opt), io_(io), slots_(slots) {
+        th_ = std::thread([this] { loop(); });
+    }
     ~DeviceWorker() { finish(); }
-    // no more batches: the thread ends once its queue is empty and its background writers are done
+    // no more batches: the thread ends once its queue is empty and its results are on disk
     void finish() {
         {
             std::lock_guard<std::mutex> l(mu_);
@@ -345,10 +467,6 @@ class DeviceWorker {
         cv_.wait(l, [this] { return !pending_; });
         pending_ = std::move(b);
         cv_.notify_all();
-    }
-    void drain() {
-        std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [this] { return !pending_ && !busy_; });
     }
     std::string error() {
         std::lock_guard<std::mutex> l(mu_);
@@ -371,6 +489,7 @@ class DeviceWorker {
                 busy_ = true;
             }
             cv_.notify_all();
+            t_wait_ += since(t_mark_);
             std::string e;
             const int n = (int)b->jobs.size();
             try {
@@ -378,6 +497,8 @@ class DeviceWorker {
             } catch (const std::exception &ex) {
                 e = ex.what();
             }
+            for (auto &j : b->jobs)
+                if (j) slots_.release(j->slot);  // (jobs that went to a writer were moved out of the batch)
             {
                 std::lock_guard<std::mutex> l(mu_);
                 if (!e.empty() && err_.empty()) err_ = e;
@@ -385,20 +506,25 @@ class DeviceWorker {
                 busy_ = false;
             }
             cv_.notify_all();
+            t_mark_ = std::chrono::steady_clock::now();
         }
-        for (auto &w : writers_)
-            if (w.valid()) {
-                try {
-                    w.get();
-                } catch (const std::exception &ex) {
-                    std::lock_guard<std::mutex> l(mu_);
-                    if (err_.empty()) err_ = ex.what();
-                }
-            }
+        for (auto &w : writers_) collect(w);
+        if (opt_.seq_stats)
+            fprintf(stderr, "device %d: waiting for batches %.3f s, uploads %.3f s, solve %.3f s, downloads %.3f s, reports + writer hand-over %.3f s\n",
+                    device_, t_wait_, t_up_, t_run_, t_down_, t_out_);
         if (solver_) faldoi_solver_destroy(solver_);
-        faldoi_pinned_free(pin_);
     }
 
+    void collect(std::future<void> &w) {
+        try {
+            if (w.valid()) w.get();
+        } catch (const std::exception &ex) {
+            std::lock_guard<std::mutex> l(mu_);
+            if (err_.empty()) err_ = ex.what();
+        }
+    }
+
+    static double since(std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
     static std::string gpu_error(int rc) { return "GPU solver failed (" + std::to_string(rc) + "): " + faldoi_last_error(); }
 
     std::string run_batch(Batch &B) {
@@ -413,71 +539,66 @@ class DeviceWorker {
                 if (rc != FALDOI_OK) return gpu_error(rc);
                 key_w_ = R0.w, key_h_ = R0.h, key_m_ = R0.method;
             }
-            // pinned staging, per slot: three frames (pd planes each; at least 2 planes so that host-preprocessed
-            // gray + Lab fit), the flow (in and out) and chi
-            const size_t size = (size_t)R0.w * R0.h, pd = R0.pd, fpl = std::max<size_t>(pd, 2);
-            const size_t per_slot = 3 * fpl * size + 2 * size + size;
-            if (per_slot * opt_.batch > pin_floats_) {
-                faldoi_pinned_free(pin_);
-                pin_ = (float *)faldoi_pinned_alloc(per_slot * opt_.batch * sizeof(float));
-                if (!pin_) return std::string("pinned staging allocation failed: ") + faldoi_last_error();
-                pin_floats_ = per_slot * opt_.batch;
-            }
             const auto t0 = std::chrono::system_clock::now();
+            auto tm = std::chrono::steady_clock::now();
             const bool occ = (R0.method == FALDOI_M_TVL1_OCC), nltv = is_nltv(R0.method);
+            // uploads: asynchronous copies out of the jobs' page-locked staging slots, preprocessing on the device
             for (int k = 0; k < n; k++) {
                 Ready &R = *B.jobs[k];
-                float *p = pin_ + per_slot * k, *pu = p + 3 * fpl * size, *pc = pu + 2 * size;
-                memcpy(pu, R.u.data(), 2 * size * sizeof(float));
-                if (occ) memcpy(pc, R.chi.data(), size * sizeof(float));
                 int rc;
                 if (opt_.host_preproc) {
                     const HostFrames F = host_preprocess(R);
-                    memcpy(p, F.i0n.data(), size * sizeof(float));
-                    memcpy(p + size, F.i1n.data(), size * sizeof(float));
-                    memcpy(p + 2 * size, F.i_1n.data(), size * sizeof(float));
-                    if (nltv) memcpy(p + 3 * size, F.lab.data(), 3 * size * sizeof(float));
-                    rc = faldoi_solver_upload(solver_, k, p, p + size, p + 2 * size, nltv ? p + 3 * size : nullptr, pu, occ ? pc : nullptr);
+                    rc = faldoi_solver_upload(solver_, k, F.i0n.data(), F.i1n.data(), F.i_1n.data(), nltv ? F.lab.data() : nullptr, R.u, occ ? R.chi : nullptr);
+                    if (rc == FALDOI_OK) rc = faldoi_solver_sync(solver_);  // F goes out of scope
                 } else {
-                    memcpy(p, R.in.i0.data.data(), pd * size * sizeof(float));
-                    memcpy(p + pd * size, R.in.i1.data.data(), pd * size * sizeof(float));
-                    memcpy(p + 2 * pd * size, R.in.i_1.data.data(), pd * size * sizeof(float));
-                    rc = faldoi_solver_upload_raw(solver_, k, p, p + pd * size, p + 2 * pd * size, (int)pd, pu, occ ? pc : nullptr);
+                    rc = faldoi_solver_upload_raw(solver_, k, R.in.i0.px(), R.in.i1.px(), R.in.i_1.px(), R.pd, R.u, occ ? R.chi : nullptr);
                 }
                 if (rc != FALDOI_OK) return gpu_error(rc);
             }
+            t_up_ += since(tm), tm = std::chrono::steady_clock::now();
             int rc = faldoi_solver_run(solver_, &R0.params, n);
             if (rc != FALDOI_OK) return gpu_error(rc);
+            if (opt_.seq_stats) faldoi_solver_sync(solver_);
+            t_run_ += since(tm), tm = std::chrono::steady_clock::now();
             for (int k = 0; k < n; k++) {
                 Ready &R = *B.jobs[k];
-                float *pu = pin_ + per_slot * k + 3 * fpl * size, *pc = pu + 2 * size;
-                rc = faldoi_solver_download(solver_, k, pu, occ ? pc : nullptr, &R.log);
+                rc = faldoi_solver_download(solver_, k, R.u, occ ? R.chi : nullptr, &R.log);
                 if (rc != FALDOI_OK) return gpu_error(rc);
-                memcpy(R.u.data(), pu, 2 * size * sizeof(float));
-                if (occ) memcpy(R.chi.data(), pc, size * sizeof(float));
             }
+            t_down_ += since(tm);
             const double secs = std::chrono::duration<double>(std::chrono::system_clock::now() - t0).count();
             for (int k = 0; k < n; k++) B.jobs[k]->secs = secs / n;
         }
+        const auto to = std::chrono::steady_clock::now();
         {
             std::lock_guard<std::mutex> l(g_io_mu);
             for (int k = 0; k < n; k++) report_job(*B.jobs[k], opt_.verbose);
         }
-        // results go to disk on background threads (at most two batches' files in flight per GPU)
-        while (writers_.size() >= 2 * (size_t)opt_.batch) {
-            writers_.front().get();
+        // results go to disk on the pool threads; a job's staging slot is free again once its files are written
+        while (writers_.size() >= 4 * (size_t)opt_.batch) {
+            collect(writers_.front());
             writers_.pop_front();
         }
         for (int k = 0; k < n; k++) {
             std::shared_ptr<Ready> job(std::move(B.jobs[k]));
-            job->in = Loaded();  // the frames are no longer needed
-            writers_.push_back(std::async(std::launch::async, [job] { save_job(*job); }));
+            SlotPool *slots = &slots_;
+            writers_.push_back(io_.submit([job, slots] {
+                struct Release {
+                    SlotPool *p;
+                    int id;
+                    ~Release() { p->release(id); }
+                } rel{slots, job->slot};
+                save_job(*job);
+            }));
         }
+        t_out_ += since(to);
         return std::string();
     }
 
     const int device_;
     const Options opt_;
+    ThreadPool &io_;
+    SlotPool &slots_;
     std::thread th_;
     std::mutex mu_;
     std::condition_variable cv_;
@@ -487,9 +608,9 @@ class DeviceWorker {
     std::string err_;
     faldoi_solver *solver_ = nullptr;
     int key_w_ = 0, key_h_ = 0, key_m_ = -1;
-    float *pin_ = nullptr;
-    size_t pin_floats_ = 0;
     std::deque<std::future<void>> writers_;
+    double t_wait_ = 0, t_up_ = 0, t_run_ = 0, t_down_ = 0, t_out_ = 0;  // -seq_stats 1
+    std::chrono::steady_clock::time_point t_mark_ = std::chrono::steady_clock::now();
 };
 
 int run_sequence(const std::string &seq_file, const std::string &argv0, const Options &opt) {
@@ -511,89 +632,97 @@ int run_sequence(const std::string &seq_file, const std::string &argv0, const Op
         }
         joblist.push_back(job);
     }
-    const size_t njobs = joblist.size();
-    std::vector<std::unique_ptr<DeviceWorker>> workers;
-    for (int d : opt.devices) workers.emplace_back(new DeviceWorker(d, opt));
-
-    // loaders: a window of jobs is being read and decoded ahead of the dispatcher, on a bounded number of threads
-    const size_t window = std::max<size_t>(2 * (size_t)opt.batch * workers.size(), 8);
-    const size_t nthreads = std::max(4u, std::min(48u, std::thread::hardware_concurrency()));
-    std::deque<std::future<Loaded>> loading;
-    size_t next_load = 0, pool_busy = 0;
-    std::mutex pool_mu;
-    std::condition_variable pool_cv;
-    auto start_load = [&](size_t k) {
-        {
-            std::unique_lock<std::mutex> l(pool_mu);
-            pool_cv.wait(l, [&] { return pool_busy < nthreads; });
-            pool_busy++;
-        }
-        return std::async(std::launch::async, [&, k] {
-            Loaded L = load_inputs(joblist[k], opt.val_method, false);
-            {
-                std::lock_guard<std::mutex> l(pool_mu);
-                pool_busy--;
-            }
-            pool_cv.notify_one();
-            return L;
-        });
-    };
-    auto refill = [&] {
-        while (next_load < njobs && loading.size() < window) loading.push_back(start_load(next_load++));
-    };
-
+    const size_t njobs = joblist.size(), ndev = opt.devices.size();
+    // per GPU: one batch on the device, one queued, one being assembled and one on its way to disk
+    SlotPool slots(std::max<size_t>(4 * (size_t)opt.batch * ndev, 8));
+    const size_t window = std::max<size_t>(2 * (size_t)opt.batch * ndev, 4);
+    ThreadPool io(std::max(4u, std::min(64u, std::thread::hardware_concurrency())));
     int rc = EXIT_SUCCESS;
-    size_t rr = 0;
-    std::unique_ptr<Batch> cur;
-    auto flush = [&] {
-        if (!cur || cur->jobs.empty()) return;
-        // an idle GPU if there is one, else round robin (submit blocks while that worker's queue slot is taken)
-        size_t pick = rr;
-        for (size_t i = 0; i < workers.size(); i++)
-            if (workers[(rr + i) % workers.size()]->idle()) {
-                pick = (rr + i) % workers.size();
-                break;
-            }
-        rr = (pick + 1) % workers.size();
-        workers[pick]->submit(std::move(cur));
-        cur.reset();
-    };
-    auto worker_failed = [&] {
-        for (auto &w : workers)
-            if (!w->error().empty()) return true;
-        return false;
-    };
-    refill();
-    for (size_t k = 0; k < njobs && rc == EXIT_SUCCESS; k++) {
-        Loaded in = loading.front().get();
-        loading.pop_front();
-        refill();
-        std::unique_ptr<Ready> R(new Ready());
-        try {
-            std::lock_guard<std::mutex> l(g_io_mu);
-            const int r = prepare_job(joblist[k], opt, std::move(in), *R);
-            if (r != EXIT_SUCCESS) rc = r;
-        } catch (const std::exception &e) {
-            fprintf(stderr, "ERROR: %s\n", e.what());
-            rc = EXIT_FAILURE;
-        }
-        if (rc != EXIT_SUCCESS || worker_failed()) break;
-        const bool fits = cur && !cur->jobs.empty() && cur->jobs[0]->w == R->w && cur->jobs[0]->h == R->h && cur->jobs[0]->pd == R->pd &&
-                          cur->jobs[0]->method == R->method && cur->jobs[0]->passthrough == R->passthrough;
-        if (!fits) flush();
-        if (!cur) cur.reset(new Batch());
-        cur->jobs.push_back(std::move(R));
-        if ((int)cur->jobs.size() == opt.batch) flush();
-    }
-    flush();  // the jobs before a failing one are completed
-    for (auto &f : loading)
-        if (f.valid()) f.wait();
-    for (auto &w : workers) w->finish();
     int done = 0;
     std::string err;
-    for (auto &w : workers) {
-        done += w->done();
-        if (err.empty()) err = w->error();
+    {
+        std::vector<std::unique_ptr<DeviceWorker>> workers;
+        for (int d : opt.devices) workers.emplace_back(new DeviceWorker(d, opt, io, slots));
+
+        struct InFlight {
+            std::future<Loaded> fut;
+            int slot;
+        };
+        std::deque<InFlight> loading;
+        size_t next_load = 0, rr = 0;
+        std::unique_ptr<Batch> cur;
+        auto start_load = [&](int slot) {
+            const size_t k = next_load++;
+            Slot *sp = slots.at(slot);
+            loading.push_back(InFlight{io.submit([&joblist, &opt, k, sp] { return load_inputs(joblist[k], opt.val_method, false, sp); }), slot});
+        };
+        auto refill = [&] {  // never blocks: decode ahead only into staging slots that are free
+            while (next_load < njobs && loading.size() < window) {
+                const int slot = slots.try_acquire();
+                if (slot < 0) break;
+                start_load(slot);
+            }
+        };
+        auto flush = [&] {
+            if (!cur || cur->jobs.empty()) return;
+            // an idle GPU if there is one, else round robin (submit blocks while that worker's queue slot is taken)
+            size_t pick = rr;
+            for (size_t i = 0; i < workers.size(); i++)
+                if (workers[(rr + i) % workers.size()]->idle()) {
+                    pick = (rr + i) % workers.size();
+                    break;
+                }
+            rr = (pick + 1) % workers.size();
+            workers[pick]->submit(std::move(cur));
+            cur.reset();
+        };
+        auto worker_failed = [&] {
+            for (auto &w : workers)
+                if (!w->error().empty()) return true;
+            return false;
+        };
+        for (size_t k = 0; k < njobs && rc == EXIT_SUCCESS; k++) {
+            refill();
+            if (loading.empty()) {
+                // every slot is taken by jobs further down the pipeline: hand over what has been assembled (so that
+                // slots are certain to come back) and wait for one
+                flush();
+                start_load(slots.acquire());
+            }
+            Loaded in = loading.front().fut.get();
+            const int slot = loading.front().slot;
+            loading.pop_front();
+            std::unique_ptr<Ready> R(new Ready());
+            R->slot = slot;
+            try {
+                std::lock_guard<std::mutex> l(g_io_mu);
+                const int r = prepare_job(joblist[k], opt, std::move(in), *R);
+                if (r != EXIT_SUCCESS) rc = r;
+            } catch (const std::exception &e) {
+                fprintf(stderr, "ERROR: %s\n", e.what());
+                rc = EXIT_FAILURE;
+            }
+            if (rc != EXIT_SUCCESS || worker_failed()) {
+                slots.release(slot);
+                break;
+            }
+            const bool fits = cur && !cur->jobs.empty() && cur->jobs[0]->w == R->w && cur->jobs[0]->h == R->h && cur->jobs[0]->pd == R->pd &&
+                              cur->jobs[0]->method == R->method && cur->jobs[0]->passthrough == R->passthrough;
+            if (!fits) flush();
+            if (!cur) cur.reset(new Batch());
+            cur->jobs.push_back(std::move(R));
+            if ((int)cur->jobs.size() == opt.batch) flush();
+        }
+        flush();  // the jobs before a failing one are completed
+        for (auto &f : loading) {
+            if (f.fut.valid()) f.fut.wait();
+            slots.release(f.slot);
+        }
+        for (auto &w : workers) w->finish();
+        for (auto &w : workers) {
+            done += w->done();
+            if (err.empty()) err = w->error();
+        }
     }
     if (!err.empty()) {
         fprintf(stderr, "ERROR: %s\n", err.c_str());
@@ -607,6 +736,10 @@ int run_sequence(const std::string &seq_file, const std::string &argv0, const Op
 }  // namespace
 
 int main(int argc, char *argv[]) {
+    // Frames and flows are multi-megabyte arrays allocated and freed at a high rate by many threads: keep them on
+    // the heap instead of one mmap/munmap pair (and its TLB shoot-down across all threads) per array.
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
     print_today();
     std::vector<std::string> args(argv, argv + argc);
     const std::string warps_val = pick_option(args, "w", "5");
@@ -619,6 +752,7 @@ int main(int argc, char *argv[]) {
     const std::string batch_str = pick_option(args, "batch", "16");
     const bool host_preproc = pick_option(args, "host_preproc", "0") == "1";
     const bool stripes = pick_option(args, "stripes", "1") != "0";
+    const bool seq_stats = pick_option(args, "seq_stats", "0") == "1";
     const std::string seq_file = pick_option(args, "seq", "");
 
     if (seq_file.empty() && args.size() != 6 && args.size() != 4) {
@@ -638,6 +772,7 @@ int main(int argc, char *argv[]) {
         // GPUs: -devices list | "all"; else -device d; else device 0.  A single call without either option may
         // use every visible GPU (row stripes of a >= 4K frame).
         const int visible = faldoi_device_count();
+        g_pinned_staging = visible > 0;
         if (devices_str == "all" || (devices_str.empty() && device_str.empty() && seq_file.empty())) {
             for (int d = 0; d < visible; d++) opt.devices.push_back(d);
         } else if (!devices_str.empty()) {
@@ -654,6 +789,7 @@ int main(int argc, char *argv[]) {
     }
     opt.host_preproc = host_preproc;
     opt.stripes = stripes;
+    opt.seq_stats = seq_stats;
     opt.file_params = file_params;
 
     int rc = EXIT_SUCCESS;

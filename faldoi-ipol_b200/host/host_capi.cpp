@@ -40,8 +40,8 @@ int faldoi_host_read_image(const char *path, float **data, int *w, int *h, int *
         *w = im.w;
         *h = im.h;
         *pd = im.pd;
-        *data = static_cast<float *>(std::malloc(im.data.size() * sizeof(float)));
-        std::memcpy(*data, im.data.data(), im.data.size() * sizeof(float));
+        *data = static_cast<float *>(std::malloc(im.count() * sizeof(float)));
+        std::memcpy(*data, im.px(), im.count() * sizeof(float));
     });
 }
 

@@ -14,11 +14,18 @@ namespace faldoi_host {
 
 namespace {
 
-std::vector<uint8_t> slurp(const std::string &path) {
+// The file's bytes, in a buffer that the calling thread reuses from file to file (a sequence decodes thousands of
+// frames on a few pool threads: fresh multi-megabyte allocations per file cost more in page faults than the decode).
+// max_bytes > 0 reads only the head of the file (header probes).
+const std::vector<uint8_t> &slurp(const std::string &path, size_t max_bytes = 0) {
+    static thread_local std::vector<uint8_t> buf;
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("cannot open '" + path + "'");
-    std::vector<uint8_t> buf;
-    if (std::fseek(f, 0, SEEK_END) == 0) {
+    buf.clear();
+    if (max_bytes) {
+        buf.resize(max_bytes);
+        buf.resize(std::fread(buf.data(), 1, max_bytes, f));
+    } else if (std::fseek(f, 0, SEEK_END) == 0) {
         const long n = std::ftell(f);
         std::rewind(f);
         if (n > 0) {
@@ -34,6 +41,18 @@ std::vector<uint8_t> slurp(const std::string &path) {
     return buf;
 }
 
+// the image's sample storage: the caller's sink when it is large enough, else the image's own vector
+float *attach(Image &im, const Sink &sink) {
+    const size_t n = im.count();
+    if (sink.ptr && sink.cap >= n) {
+        im.ext = sink.ptr;
+        return im.ext;
+    }
+    im.ext = nullptr;
+    im.data.resize(n);
+    return im.data.data();
+}
+
 uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
 
 // ---------------------------------------------------------------- PNG
@@ -44,18 +63,23 @@ inline int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : bc;
 }
 
-Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
+Image read_png(const std::vector<uint8_t> &buf, const std::string &path, const Sink &sink, bool header_only) {
     auto bad = [&](const char *why) { return std::runtime_error("PNG '" + path + "': " + why); };
     if (buf.size() < 33) throw bad("truncated");
     size_t pos = 8;
     uint32_t w = 0, h = 0;
     int depth = 0, ctype = 0, interlace = 0;
-    std::vector<uint8_t> idat, plte;
+    static thread_local std::vector<uint8_t> idat, raw, pix, zero_row;  // reused from file to file by this thread
+    std::vector<uint8_t> plte;
+    idat.clear();
     bool have_ihdr = false;
     while (pos + 12 <= buf.size()) {
         const uint32_t len = be32(&buf[pos]);
         const char *type = (const char *)&buf[pos + 4];
-        if (pos + 12 + len > buf.size()) throw bad("truncated chunk");
+        if (pos + 12 + len > buf.size()) {
+            if (header_only && have_ihdr) break;
+            throw bad("truncated chunk");
+        }
         const uint8_t *d = &buf[pos + 8];
         if (!memcmp(type, "IHDR", 4)) {
             if (len < 13) throw bad("bad IHDR");
@@ -90,17 +114,22 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
         default: throw bad("unknown colour type");
     }
     if (!depth_ok) throw bad("bit depth not allowed for this colour type");
+    if (header_only) {
+        Image hdr;
+        hdr.w = (int)w, hdr.h = (int)h, hdr.pd = (ctype == 3) ? 3 : channels;
+        return hdr;
+    }
     const size_t bpp_bits = (size_t)channels * depth;
     const size_t stride = (w * bpp_bits + 7) / 8;
     const size_t bpp = (bpp_bits + 7) / 8;  // filter unit in bytes
-    std::vector<uint8_t> raw((stride + 1) * h);
+    raw.resize((stride + 1) * h);
     uLongf outlen = raw.size();
     if (uncompress(raw.data(), &outlen, idat.data(), idat.size()) != Z_OK || outlen != raw.size())
         throw bad("zlib inflate failed");
     // undo the scanline filters (one specialised loop per filter type; the first `bpp` bytes of a row have
     // no left neighbour)
-    std::vector<uint8_t> pix(stride * h);
-    const std::vector<uint8_t> zero_row(stride, 0);
+    pix.resize(stride * h);
+    zero_row.assign(stride, 0);
     for (uint32_t y = 0; y < h; y++) {
         const uint8_t ft = raw[y * (stride + 1)];
         const uint8_t *in = &raw[y * (stride + 1) + 1];
@@ -133,10 +162,10 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
     const bool pal = (ctype == 3);
     im.pd = pal ? 3 : channels;
     const size_t n = (size_t)w * h;
-    im.data.assign(n * im.pd, 0.f);
+    float *out = attach(im, sink);
     if (depth == 8 && !pal) {  // the common case (8-bit gray / RGB / RGBA): straight de-interleave
         for (int c = 0; c < channels; c++) {
-            float *dst = &im.data[c * n];
+            float *dst = out + c * n;
             for (uint32_t y = 0; y < h; y++) {
                 const uint8_t *row = &pix[y * stride] + c;
                 float *d = dst + (size_t)y * w;
@@ -161,9 +190,9 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
                 }
                 if (pal) {
                     if (3 * v + 2 >= plte.size()) throw bad("palette index out of range");
-                    for (int k = 0; k < 3; k++) im.data[k * n + (size_t)y * w + x] = plte[3 * v + k];
+                    for (int k = 0; k < 3; k++) out[k * n + (size_t)y * w + x] = plte[3 * v + k];
                 } else {
-                    im.data[c * n + (size_t)y * w + x] = (float)v;
+                    out[c * n + (size_t)y * w + x] = (float)v;
                 }
             }
     }
@@ -171,7 +200,7 @@ Image read_png(const std::vector<uint8_t> &buf, const std::string &path) {
 }
 
 // ---------------------------------------------------------------- PNM
-Image read_pnm(const std::vector<uint8_t> &buf, const std::string &path) {
+Image read_pnm(const std::vector<uint8_t> &buf, const std::string &path, const Sink &sink, bool header_only) {
     auto bad = [&](const char *why) { return std::runtime_error("PNM '" + path + "': " + why); };
     const int kind = buf[1] - '0';
     if (kind < 1 || kind > 6) throw bad("unsupported magic");
@@ -197,11 +226,12 @@ Image read_pnm(const std::vector<uint8_t> &buf, const std::string &path) {
     const long maxv = bitmap ? 1 : next_int();
     im.pd = (kind == 3 || kind == 6) ? 3 : 1;
     if (im.w <= 0 || im.h <= 0 || maxv <= 0 || maxv > 65535) throw bad("bad header");
+    if (header_only) return im;
     const size_t n = (size_t)im.w * im.h;
-    im.data.assign(n * im.pd, 0.f);
+    float *out = attach(im, sink);
     if (kind <= 3) {
         for (size_t i = 0; i < n; i++)
-            for (int c = 0; c < im.pd; c++) im.data[c * n + i] = (float)(bitmap ? 1 - next_int() : next_int());
+            for (int c = 0; c < im.pd; c++) out[c * n + i] = (float)(bitmap ? 1 - next_int() : next_int());
         return im;
     }
     pos++;  // single whitespace after the header
@@ -209,21 +239,29 @@ Image read_pnm(const std::vector<uint8_t> &buf, const std::string &path) {
         const size_t stride = (im.w + 7) / 8;
         if (pos + stride * im.h > buf.size()) throw bad("truncated");
         for (int y = 0; y < im.h; y++)
-            for (int x = 0; x < im.w; x++) im.data[(size_t)y * im.w + x] = 1.f - ((buf[pos + y * stride + x / 8] >> (7 - x % 8)) & 1);
+            for (int x = 0; x < im.w; x++) out[(size_t)y * im.w + x] = 1.f - ((buf[pos + y * stride + x / 8] >> (7 - x % 8)) & 1);
         return im;
     }
     const int bps = maxv > 255 ? 2 : 1;
     if (pos + n * im.pd * bps > buf.size()) throw bad("truncated");
+    if (bps == 1 && im.pd == 3) {  // the common case, binary 8-bit RGB: one pass per plane keeps the stores sequential
+        const uint8_t *src = &buf[pos];
+        for (int c = 0; c < 3; c++) {
+            float *dst = out + c * n;
+            for (size_t i = 0; i < n; i++) dst[i] = (float)src[3 * i + c];
+        }
+        return im;
+    }
     for (size_t i = 0; i < n; i++)
         for (int c = 0; c < im.pd; c++) {
             const uint8_t *p = &buf[pos + (i * im.pd + c) * bps];
-            im.data[c * n + i] = (float)(bps == 2 ? (p[0] << 8 | p[1]) : p[0]);
+            out[c * n + i] = (float)(bps == 2 ? (p[0] << 8 | p[1]) : p[0]);
         }
     return im;
 }
 
 // ---------------------------------------------------------------- .flo ("PIEH", w, h, interleaved u,v)
-Image read_flo(const std::vector<uint8_t> &buf, const std::string &path) {
+Image read_flo(const std::vector<uint8_t> &buf, const std::string &path, const Sink &sink, bool header_only) {
     int32_t wh[2];
     memcpy(wh, &buf[4], 8);
     Image im;
@@ -231,14 +269,16 @@ Image read_flo(const std::vector<uint8_t> &buf, const std::string &path) {
     im.h = wh[1];
     im.pd = 2;
     const size_t n = (size_t)im.w * im.h;
-    if (im.w <= 0 || im.h <= 0 || buf.size() < 12 + n * 8) throw std::runtime_error(".flo '" + path + "': truncated");
-    im.data.resize(2 * n);
+    if (im.w <= 0 || im.h <= 0) throw std::runtime_error(".flo '" + path + "': bad header");
+    if (header_only) return im;
+    if (buf.size() < 12 + n * 8) throw std::runtime_error(".flo '" + path + "': truncated");
+    float *out = attach(im, sink);
     const float *f = (const float *)&buf[12];
     for (size_t i = 0; i < n; i++) {
         float uv[2];
         memcpy(uv, f + 2 * i, 8);
-        im.data[i] = uv[0];
-        im.data[n + i] = uv[1];
+        out[i] = uv[0];
+        out[n + i] = uv[1];
     }
     return im;
 }
@@ -263,13 +303,20 @@ void put_chunk(std::ofstream &f, const char *type, const std::vector<uint8_t> &d
 
 }  // namespace
 
-Image read_image_split(const std::string &path) {
-    const std::vector<uint8_t> buf = slurp(path);
+static Image read_any(const std::string &path, const Sink &sink, bool header_only) {
+    const std::vector<uint8_t> &buf = slurp(path, header_only ? 4096 : 0);
     static const uint8_t png_magic[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    if (buf.size() >= 8 && !memcmp(buf.data(), png_magic, 8)) return read_png(buf, path);
-    if (buf.size() >= 12 && !memcmp(buf.data(), "PIEH", 4)) return read_flo(buf, path);
-    if (buf.size() >= 7 && buf[0] == 'P' && buf[1] >= '1' && buf[1] <= '6') return read_pnm(buf, path);
+    if (buf.size() >= 8 && !memcmp(buf.data(), png_magic, 8)) return read_png(buf, path, sink, header_only);
+    if (buf.size() >= 12 && !memcmp(buf.data(), "PIEH", 4)) return read_flo(buf, path, sink, header_only);
+    if (buf.size() >= 7 && buf[0] == 'P' && buf[1] >= '1' && buf[1] <= '6') return read_pnm(buf, path, sink, header_only);
     throw std::runtime_error("'" + path + "': unsupported image format (PNG, PNM and .flo are supported)");
+}
+
+Image read_image_split(const std::string &path, Sink sink) { return read_any(path, sink, false); }
+
+void probe_image(const std::string &path, int *w, int *h, int *pd) {
+    const Image im = read_any(path, Sink(), true);
+    *w = im.w, *h = im.h, *pd = im.pd;
 }
 
 void write_flo(const std::string &path, const float *u1, const float *u2, int w, int h) {

@@ -8,13 +8,28 @@
 
 namespace faldoi_host {
 
+// Where the samples of a decoded image go: by default the image's own vector; a caller may hand in storage of its
+// own (e.g. a page-locked staging buffer) so that decoding writes straight into it.  Storage that is too small
+// for the file is ignored (the image then owns its samples as usual).
+struct Sink {
+    float *ptr = nullptr;
+    size_t cap = 0;  // floats
+};
+
 struct Image {
     int w = 0, h = 0, pd = 0;
     std::vector<float> data;  // planar ("split"): data[c*w*h + j*w + i], sample values as stored (0..255 for 8 bit)
+    float *ext = nullptr;     // set instead of `data` when the samples were decoded into a caller's Sink
+    const float *px() const { return ext ? ext : data.data(); }
+    float *px() { return ext ? ext : data.data(); }
+    size_t count() const { return (size_t)w * h * pd; }
+    bool empty() const { return count() == 0; }
 };
 
 // Throws std::runtime_error with a message naming the file on any failure.
-Image read_image_split(const std::string &path);        // dispatch on magic bytes: PNG, PNM, .flo
+Image read_image_split(const std::string &path, Sink sink = Sink());  // dispatch on magic bytes: PNG, PNM, .flo
+// Header only: size and channel count as read_image_split would report them.
+void probe_image(const std::string &path, int *w, int *h, int *pd);
 void write_flo(const std::string &path, const float *u1, const float *u2, int w, int h);
 void write_png_gray8(const std::string &path, const int *values, int w, int h);  // values clipped to 0..255
 void write_image_float_split(const std::string &path, const float *planes, int w, int h, int pd);  // .flo (pd=2) only

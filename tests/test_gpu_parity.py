@@ -107,6 +107,7 @@ def test_reference_signature_mirrors(fb, po):
     fb.tvl2OF(g["I0n"], g["I1n"].copy(), u1, u2, *xi, 40.0, 0.3, 0.125, 0.01, w, h, 3, 0)
     assert np.array_equal(np.stack([u1, u2]), g["u_m0_w3"])
     u1, u2 = g["u0"][0].copy(), g["u0"][1].copy()
+    xi = [np.zeros((h, w), np.float32) for _ in range(4)]  # in/out arguments: the call above left its final duals in them
     fb.tvcsad_PD(g["I0n"], g["I1n"].copy(), *xi, 0.85, 0.3, 0.125, 0.01, w, h, 1, 0, u1, u2)
     assert np.array_equal(np.stack([u1, u2]), g["u_m4_w1"])
     u1, u2 = g["u0"][0].copy(), g["u0"][1].copy()

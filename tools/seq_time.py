@@ -8,6 +8,7 @@ What the pipeline does per pair: read + decode 3 frames and a flow (host thread 
 solver handle through pinned staging, solve, download, write the .flo on a background thread.
 """
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -52,11 +53,12 @@ def main():
         for jobs in (min(4, n), n):
             open(os.path.join(t, "jobs.txt"), "w").write("".join(lines[:jobs]))
             t0 = time.perf_counter()
-            r = subprocess.run([BIN, "-seq", os.path.join(t, "jobs.txt"), "-m", method, "-w", "5", "-devices", devices, "-batch", batch],
+            r = subprocess.run([BIN, "-seq", os.path.join(t, "jobs.txt"), "-m", method, "-w", "5", "-devices", devices, "-batch", batch, "-seq_stats", "1"],
                                capture_output=True, text=True)
             res[jobs] = time.perf_counter() - t0
             assert r.returncode == 0 and ("sequence: %d pairs done" % jobs) in r.stderr, r.stderr[-2000:]
             print("%d pairs on devices %s, batch %s: %.2f s wall" % (jobs, devices, batch, res[jobs]), flush=True)
+            print("".join(m + "\n" for m in re.findall(r"device \d+: waiting[^\n]*", r.stderr)), end="")
         if n > 4:
             dt = res[n] - res[min(4, n)]
             print("marginal: %.4f s per pair = %.1f pairs/s (start-up + first 4 pairs: %.2f s)" % (dt / (n - 4), (n - 4) / dt, res[4]))
