@@ -197,15 +197,20 @@ static int make_plane_map(CUtensorMap *out, float *base, const Geo &g, size_t np
 static int make_tile_maps(faldoi_solver *s) {
     const Geo &g = s->g;
     const size_t nstate = (size_t)2 * ST_COUNT * g.B;
-    float *c0 = method_is_csad(s->method) ? s->scale : s->rho_c;
+    float *c0 = s->rho_c;
     int rc;
-    if ((rc = make_plane_map(&s->maps.ub, s->state, g, nstate, TT_PW, TT_UB_ROWS))) return rc;
-    if ((rc = make_plane_map(&s->maps.xi, s->state, g, nstate, TT_PW, TT_XI_ROWS))) return rc;
-    if ((rc = make_plane_map(&s->maps.pl, s->state, g, nstate, TT_W, TT_H))) return rc;
-    if ((rc = make_plane_map(&s->maps.c0, c0, g, g.B, TT_W, TT_H))) return rc;
-    if ((rc = make_plane_map(&s->maps.ix, s->Ix, g, g.B, TT_W, TT_H))) return rc;
-    if ((rc = make_plane_map(&s->maps.iy, s->Iy, g, g.B, TT_W, TT_H))) return rc;
-    if (method_is_csad(s->method) && (rc = make_plane_map(&s->maps.sep, s->csad_sep, g, (size_t)CSAD_SEPS * g.B, TT_W, TT_H))) return rc;
+    if (method_is_csad(s->method)) {  // boxes of the two-iteration TV-CSAD kernel
+        if ((rc = make_plane_map(&s->cmaps.ub, s->state, g, nstate, C2_PW, C2_UB_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.xi, s->state, g, nstate, C2_PW, C2_XI_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.pl, s->state, g, nstate, C2_PW, C2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.sc, s->scale, g, g.B, C2_PW, C2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.ix, s->Ix, g, g.B, C2_PW, C2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.iy, s->Iy, g, g.B, C2_PW, C2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.t1, s->csad_t1, g, g.B, C2_PW, C2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.t2, s->csad_t2, g, g.B, C2_PW, C2_PL_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.i0, s->I0, g, g.B, C2_TP, C2_T_ROWS))) return rc;
+        if ((rc = make_plane_map(&s->cmaps.iw, s->I1w, g, g.B, C2_TP, C2_T_ROWS))) return rc;
+    }
     if (!method_is_csad(s->method)) {  // boxes of the two-iteration kernel (2-pixel apron)
         if ((rc = make_plane_map(&s->maps2.ub, s->state, g, nstate, T2_PW, T2_UB_ROWS))) return rc;
         if ((rc = make_plane_map(&s->maps2.xi, s->state, g, nstate, T2_PW, T2_XI_ROWS))) return rc;
@@ -295,8 +300,15 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
         if (method_is_csad(method)) {
             ALLOC(s->scale, B * P);
             ALLOC(s->I1w, B * P);
-            ALLOC(s->csad_blk, CSAD_FLOATS * B * P);
-            ALLOC(s->csad_sep, CSAD_SEPS * B * P);
+            if (fam == FAM_TV) {  // TV-CSAD: rank order of the neighbour residuals (tv_csad2_kernel.cuh)
+                ALLOC(s->csad_t1, B * P);
+                ALLOC(s->csad_t2, B * P);
+                s->csad_perm = (unsigned *)s->dmalloc((size_t)C2_WORDS * B * P);
+                if (!s->csad_perm) return fail(FALDOI_ERR_MEM);
+            } else {  // NLTV-CSAD: two-level sorted residual table (csad_select)
+                ALLOC(s->csad_blk, CSAD_FLOATS * B * P);
+                ALLOC(s->csad_sep, CSAD_SEPS * B * P);
+            }
         } else {
             ALLOC(s->rho_c, B * P);
         }
@@ -322,9 +334,7 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
     }
 #undef ALLOC
     // function attributes are per device: opt the tile kernels into 97 KB of dynamic shared memory here
-    if (!cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_TVL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 128),
-                 "cudaFuncSetAttribute") ||
-        !cuda_ok(cudaFuncSetAttribute(tv_tile_kernel<DATA_CSAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename TileSmemFor<DATA_CSAD>::type) + 128),
+    if (!cuda_ok(cudaFuncSetAttribute(tv_csad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Csad2Smem) + 128),
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(tv_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
                  "cudaFuncSetAttribute") ||
@@ -562,6 +572,19 @@ __global__ void count_active2_kernel(const unsigned *err_max, const unsigned cha
     *out = n;
 }
 
+// the same with TV-CSAD's mean error (tv_csad2_kernel)
+__global__ void count_active2_sum_kernel(const double *err_sum, const unsigned char *stat, int stat_stride, int npairs, int max_iters,
+                                         int L, float tol2, float npix, int *out) {
+    int n = 0;
+    for (int b = 0; b < npairs; b++) {
+        const double *e = err_sum + (size_t)b * max_iters + 2 * L;
+        bool act = stat[(size_t)b * stat_stride + L] && (float)e[0] / npix > tol2;
+        if (act && 2 * L + 1 < max_iters) act = (float)e[1] / npix > tol2;
+        n += act;
+    }
+    *out = n;
+}
+
 __global__ void export_flow_kernel(const float *state, size_t set_stride, const int *parity, float *packed, Geo g) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -602,11 +625,6 @@ static int make_div_const(faldoi_solver *s, float b, DivConst *out) {
     return FALDOI_OK;
 }
 
-static void launch_csad_iter(faldoi_solver *s, const TvArgs &a, int it, int npairs) {
-    const dim3 grid((s->g.pitch + TT_W - 1) / TT_W, (s->g.h + TT_H - 1) / TT_H, npairs);
-    tv_tile_kernel<DATA_CSAD><<<grid, TT_THREADS, sizeof(typename TileSmemFor<DATA_CSAD>::type) + 128, s->stream>>>(s->maps, a, it);
-}
-
 static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     const Geo g = s->g;
     const bool csad = method_is_csad(s->method);
@@ -621,8 +639,6 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.Iy = s->Iy;
     a.rho_c = s->rho_c;
     a.scale = s->scale;
-    a.blk = s->csad_blk;
-    a.sep = s->csad_sep;
     a.err_max = s->err_max;
     a.err_chk = s->err_max;
     a.err_sum = s->err_sum;
@@ -634,8 +650,8 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
     a.l_t = p->lambda * p->theta;
     a.tol2 = p->tol * p->tol;
     if (int rc = make_div_const(s, p->theta, &a.dth)) return rc;
-    const bool use_t2 = !csad;  // TVL2: two iterations per HBM pass (tv_tile2_kernel); TV-CSAD: one (tv_tile_kernel<CSAD>)
-    if (use_t2) {
+    // Both models run two iterations per HBM pass (tv_tile2_kernel / tv_csad2_kernel); stat[b][L] = launch L ran normally
+    {
         const int need = p->max_iters / 2 + 4;
         if (need > s->t2_stride) {
             s->t2_stat = (unsigned char *)s->dmalloc(((size_t)g.B * need + 3) / 4);
@@ -668,7 +684,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         warp_constants_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(wa);
         s->launches++;
         if (csad) {
-            CsadArgs ca{};
+            CsadPermArgs ca{};
             ca.I0 = s->I0;
             ca.I1w = s->I1w;
             ca.Ix = s->Ix;
@@ -678,56 +694,46 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
             ca.parity = s->parity;
             ca.set_stride = s->set_stride;
             ca.scale = s->scale;
-            ca.blk = s->csad_blk;
-            ca.sep = s->csad_sep;
+            ca.t1 = s->csad_t1;
+            ca.t2 = s->csad_t2;
+            ca.perm = s->csad_perm;
             ca.g = g;
-            ca.hyp = 1;
             const dim3 cb(32, 4);
-            csad_constants_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
+            csad_perm_kernel<<<grid2d(g, cb, npairs), cb, 0, s->stream>>>(ca);
             s->launches++;
         }
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         // All launches of a warp are enqueued without waiting for results; converged pairs return at
         // once.  To stop enqueuing once EVERY pair has met the exit test, the active-pair count is
-        // copied to pinned memory every CHUNK launches and inspected two chunks later (so the GPU
+        // copied to pinned memory every LCHUNK launches and inspected two chunks later (so the GPU
         // always has at least one full chunk queued and never waits for the host).
-        if (use_t2) {
-            // two iterations per launch: ceil(max_iters/2) launches + one slot for a trailing fix-up
-            const int nL = (p->max_iters + 1) / 2 + 1, LCHUNK = 13;
-            FALDOI_CUDA(cudaMemsetAsync(s->t2_stat, 0, (size_t)g.B * s->t2_stride, s->stream));
-            const dim3 grid((g.pitch + T2_W - 1) / T2_W, (g.h + T2_H - 1) / T2_H, npairs);
-            T2Args t2{s->t2_stat, s->t2_stride};
-            for (int c = 0, L = 0; L < nL; c++) {
-                if (c >= 2) {
-                    FALDOI_CUDA(cudaEventSynchronize(s->chunk_ev[(c - 2) & 3]));
-                    if (s->h_active[(c - 2) & 3] == 0) break;
-                }
-                const int end = (L + LCHUNK < nL) ? L + LCHUNK : nL;
-                for (; L < end; L++) {
-                    tv_tile2_kernel<<<grid, T2_THREADS, sizeof(Tile2Smem) + 128, s->stream>>>(s->maps2, a, t2, L);
-                    s->launches++;
-                }
-                const int Lc = (L - 1 < (p->max_iters + 1) / 2) ? L - 1 : (p->max_iters + 1) / 2 - 1;
-                count_active2_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->t2_stat, s->t2_stride, npairs, p->max_iters, Lc, a.tol2,
-                                                             s->d_active + (c & 3));
-                FALDOI_CUDA(cudaMemcpyAsync(s->h_active + (c & 3), s->d_active + (c & 3), sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-                FALDOI_CUDA(cudaEventRecord(s->chunk_ev[c & 3], s->stream));
-                s->launches++;
-            }
-        }
-        const int CHUNK = 25;
-        for (int c = 0, it = 0; !use_t2 && it < p->max_iters; c++) {
+        // Two iterations per launch: ceil(max_iters/2) launches + one slot for a trailing fix-up.
+        const int nL = (p->max_iters + 1) / 2 + 1, LCHUNK = 13;
+        FALDOI_CUDA(cudaMemsetAsync(s->t2_stat, 0, (size_t)g.B * s->t2_stride, s->stream));
+        const dim3 grid((g.pitch + T2_W - 1) / T2_W, (g.h + T2_H - 1) / T2_H, npairs);
+        const dim3 cgrid((g.pitch + C2_W - 1) / C2_W, (g.h + C2_H - 1) / C2_H, npairs);
+        const T2Args t2{s->t2_stat, s->t2_stride};
+        const Csad2Args c2{s->csad_perm, s->t2_stat, s->t2_stride};
+        for (int c = 0, L = 0; L < nL; c++) {
             if (c >= 2) {
                 FALDOI_CUDA(cudaEventSynchronize(s->chunk_ev[(c - 2) & 3]));
                 if (s->h_active[(c - 2) & 3] == 0) break;
             }
-            const int end = (it + CHUNK < p->max_iters) ? it + CHUNK : p->max_iters;
-            for (; it < end; it++) {
-                launch_csad_iter(s, a, it, npairs);
+            const int end = (L + LCHUNK < nL) ? L + LCHUNK : nL;
+            for (; L < end; L++) {
+                if (csad)
+                    tv_csad2_kernel<<<cgrid, C2_THREADS, sizeof(Csad2Smem) + 128, s->stream>>>(s->cmaps, a, c2, L);
+                else
+                    tv_tile2_kernel<<<grid, T2_THREADS, sizeof(Tile2Smem) + 128, s->stream>>>(s->maps2, a, t2, L);
                 s->launches++;
             }
-            count_active_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->err_sum, 1, npairs, p->max_iters, it - 1, a.tol2,
-                                                        (float)(g.w * g.h), s->d_active + (c & 3));
+            const int Lc = (L - 1 < (p->max_iters + 1) / 2) ? L - 1 : (p->max_iters + 1) / 2 - 1;
+            if (csad)
+                count_active2_sum_kernel<<<1, 1, 0, s->stream>>>(s->err_sum, s->t2_stat, s->t2_stride, npairs, p->max_iters, Lc, a.tol2,
+                                                                 (float)(g.w * g.h), s->d_active + (c & 3));
+            else
+                count_active2_kernel<<<1, 1, 0, s->stream>>>(s->err_max, s->t2_stat, s->t2_stride, npairs, p->max_iters, Lc, a.tol2,
+                                                             s->d_active + (c & 3));
             FALDOI_CUDA(cudaMemcpyAsync(s->h_active + (c & 3), s->d_active + (c & 3), sizeof(int), cudaMemcpyDeviceToHost, s->stream));
             FALDOI_CUDA(cudaEventRecord(s->chunk_ev[c & 3], s->stream));
             s->launches++;
@@ -735,7 +741,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         if (s->phase_mark()) return FALDOI_ERR_CUDA;
         finalize_warp_kernel<<<(npairs + 63) / 64, 64, 0, s->stream>>>(s->err_max, s->err_sum, csad ? 1 : 0, 0, s->parity,
                                                                        s->log_iters, s->log_err, p->max_iters, a.tol2,
-                                                                       (float)(g.w * g.h), wp, npairs, use_t2 ? 2 : 1);
+                                                                       (float)(g.w * g.h), wp, npairs, 2);
         s->launches++;
     }
     export_flow_kernel<<<grid2d(g, blk, npairs), blk, 0, s->stream>>>(s->state, s->set_stride, s->parity, s->packed, g);

@@ -28,25 +28,32 @@ namespace faldoi {
 // Stages of the ring x resident CTAs per SM (register budget).  Measured, 4 pairs, exact / fast mode:
 // 2x3 (62 KB, 80 registers) 5.03 / 10.6 Gpix*iter/s, 4x2 (102 KB, 107 registers) 4.76 / 10.7, 3x2 4.80, 2x2 4.84.
 #ifndef FALDOI_NLT_STAGES
-#define FALDOI_NLT_STAGES 2
+#define FALDOI_NLT_STAGES 3
 #endif
 #ifndef FALDOI_NLT_CTAS
-#define FALDOI_NLT_CTAS 3
+#define FALDOI_NLT_CTAS 2
 #endif
 #ifndef FALDOI_NLT_H
-#define FALDOI_NLT_H 8  // tile rows = warps per CTA
+#define FALDOI_NLT_H 8  // tile rows
+#endif
+#ifndef FALDOI_NLT_V
+#define FALDOI_NLT_V 2  // pixels per lane (4: one warp per tile row; 2: two warps per row, half the registers per thread)
 #endif
 enum {
     NLT_W = 128,
     NLT_H = FALDOI_NLT_H,
     NLT_PW = NLT_W + 8,   // apron tile: cols x0-4 .. x0+131
     NLT_AR = NLT_H + 4,   // apron tile: rows y0-2 .. y0+NLT_H+1
-    NLT_THREADS = 32 * NLT_H,
+    NLT_V = FALDOI_NLT_V,
+    NLT_WPR = 4 / NLT_V,              // warps per tile row
+    NLT_WARPS = NLT_H * NLT_WPR,
+    NLT_THREADS = 32 * NLT_WARPS,
     NLT_NS = FALDOI_NLT_STAGES,
     NLT_TILE = NLT_W * NLT_H,
     NLT_RTILE = NLT_PW * NLT_H,  // reciprocal-dual box: cols x0-4 .. x0+131
     NLT_APRON = NLT_AR * NLT_PW
 };
+static_assert(NLT_V == 4 || NLT_V == 2, "FALDOI_NLT_V must be 4 or 2");
 static_assert((NLT_APRON * 4) % 128 == 0 && (NLT_RTILE * 4) % 128 == 0, "every TMA destination must keep 128-byte alignment");
 
 struct NlTileSmem {
@@ -54,7 +61,7 @@ struct NlTileSmem {
     float rec[NLT_NS][2][NLT_RTILE];  // P[23-s], Q[23-s], rows shifted by k, cols x0-4 ..
     float ub[2][NLT_APRON];
     float rw[NLT_APRON];
-    double red[NLT_H];
+    double red[NLT_WARPS];
     unsigned long long full[NLT_NS], cbar;
 };
 
@@ -91,22 +98,44 @@ __host__ __device__ constexpr int nl_step_slot(int step) {
     return PAIRED ? ((step & 1) ? NL_SLOTS - 1 - (step >> 1) : (step >> 1)) : step;
 }
 
-// out[i] = row[i + l], l in -2..2 known at compile time after unrolling: two aligned float4 loads and a
-// static pick instead of four scalar loads (which would be 4-way bank conflicts at a lane stride of 4)
-__device__ __forceinline__ void nl_shifted4(const float *row, int l, float (&out)[4]) {
-    const float4 M = *reinterpret_cast<const float4 *>(row);
-    if (l == 0) {
-        out[0] = M.x, out[1] = M.y, out[2] = M.z, out[3] = M.w;
-    } else if (l < 0) {
-        const float4 L = *reinterpret_cast<const float4 *>(row - 4);
-        const float t[8] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = t[4 + i + l];
+// aligned vector access of V consecutive floats (float4 / float2)
+template <int V>
+__device__ __forceinline__ void nl_ld(const float *p, float (&o)[V]) {
+    if (V == 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(p);
+        o[0] = q.x, o[1] = q.y, o[2 % V] = q.z, o[3 % V] = q.w;
     } else {
-        const float4 H = *reinterpret_cast<const float4 *>(row + 4);
-        const float t[8] = {M.x, M.y, M.z, M.w, H.x, H.y, H.z, H.w};
+        const float2 q = *reinterpret_cast<const float2 *>(p);
+        o[0] = q.x, o[1] = q.y;
+    }
+}
+template <int V>
+__device__ __forceinline__ void nl_st(float *p, const float (&o)[V]) {
+    if (V == 4)
+        *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2 % V], o[3 % V]);
+    else
+        *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1]);
+}
+
+// out[i] = row[i + l], l in -2..2 known at compile time after unrolling: two aligned vector loads and a
+// static pick instead of V scalar loads (which would be V-way bank conflicts at a lane stride of V)
+template <int V>
+__device__ __forceinline__ void nl_shifted(const float *row, int l, float (&out)[V]) {
+    float m[V];
+    nl_ld<V>(row, m);
+    if (l == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = t[i + l];
+        for (int i = 0; i < V; i++) out[i] = m[i];
+    } else if (l < 0) {
+        float lo[V];
+        nl_ld<V>(row - V, lo);
+#pragma unroll
+        for (int i = 0; i < V; i++) out[i] = (i + l < 0) ? lo[(V + i + l) % V] : m[(i + l + V) % V];
+    } else {
+        float hi[V];
+        nl_ld<V>(row + V, hi);
+#pragma unroll
+        for (int i = 0; i < V; i++) out[i] = (i + l >= V) ? hi[(i + l) % V] : m[(i + l) % V];
     }
 }
 
@@ -130,7 +159,9 @@ template <int DATA, bool EXACT>
 __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel(const __grid_constant__ NlTileMaps maps, NlArgs a, int it, int base_parity) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     NlTileSmem &S = *reinterpret_cast<NlTileSmem *>(smem_raw);
-    const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
+    constexpr int V = NLT_V;
+    const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+    const int r = wi / NLT_WPR, col0 = V * ((wi % NLT_WPR) * 32 + lane);  // tile row, first tile column of this lane's pixels
     const int w = a.g.w, h = a.g.h, pitch = a.g.pitch, B = a.g.B;
     const int x0 = blockIdx.x * NLT_W, y0 = blockIdx.y * NLT_H;
     const int par = (base_parity + it) & 1;
@@ -163,7 +194,7 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
     }
     __syncthreads();  // barrier objects are initialised for everyone
 
-    const int y = y0 + r, gx0 = x0 + 4 * lane;
+    const int y = y0 + r, gx0 = x0 + col0;
     const bool act = (y < h) && (gx0 < w);
     const size_t plane = a.g.plane, ks = (size_t)B * plane, off = (size_t)b * plane;
     const size_t o = (size_t)y * pitch + gx0;
@@ -173,16 +204,18 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
     const float tau = a.tau, l_t = a.l_t;
 
     // ---- own pixel data and the data term (plain coalesced float4 loads, once per tile) ----
-    float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f}, dv1[4] = {0.f, 0.f, 0.f, 0.f}, dv2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (act) {
-        const float4 U1 = ld4(sin + ST_U1 * ks + o), U2 = ld4(sin + ST_U2 * ks + o);
-        const float4 IX = ld4(a.Ix + off + o), IY = ld4(a.Iy + off + o);
-        const float4 C0 = ld4((DATA == DATA_TVL1 ? a.rho_c : a.scale) + off + o);
-        const float ix[4] = {IX.x, IX.y, IX.z, IX.w}, iy[4] = {IY.x, IY.y, IY.z, IY.w}, cc[4] = {C0.x, C0.y, C0.z, C0.w};
-        u1[0] = U1.x, u1[1] = U1.y, u1[2] = U1.z, u1[3] = U1.w;
-        u2[0] = U2.x, u2[1] = U2.y, u2[2] = U2.z, u2[3] = U2.w;
+    float u1[V], u2[V], dv1[V], dv2[V];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < V; i++) u1[i] = u2[i] = dv1[i] = dv2[i] = 0.f;
+    if (act) {
+        float ix[V], iy[V], cc[V];
+        nl_ld<V>(sin + ST_U1 * ks + o, u1);
+        nl_ld<V>(sin + ST_U2 * ks + o, u2);
+        nl_ld<V>(a.Ix + off + o, ix);
+        nl_ld<V>(a.Iy + off + o, iy);
+        nl_ld<V>((DATA == DATA_TVL1 ? a.rho_c : a.scale) + off + o, cc);
+#pragma unroll
+        for (int i = 0; i < V; i++) {
             float v1, v2;
             if (DATA == DATA_TVL1) {
                 const float grad = ix[i] * ix[i] + iy[i] * iy[i];
@@ -220,24 +253,27 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
 
     // ---- apron planes: own ubar and 1/wt ----
     mbar_wait(&S.cbar, 0);
-    const int ac = (r + 2) * NLT_PW + 4 + 4 * lane;  // this quad in the apron tiles
-    const float4 C1 = *reinterpret_cast<const float4 *>(&S.ub[0][ac]), C2 = *reinterpret_cast<const float4 *>(&S.ub[1][ac]);
-    const float4 RW = *reinterpret_cast<const float4 *>(&S.rw[ac]);
+    const int ac = (r + 2) * NLT_PW + 4 + col0;  // this lane's pixels in the apron tiles
     // rwp: 1/wt of the own pixels (fast) or wt itself (exact; 1 in the pitch padding, where wt is 0 and every weight too)
-    const float c1[4] = {C1.x, C1.y, C1.z, C1.w}, c2[4] = {C2.x, C2.y, C2.z, C2.w};
-    float rwp[4] = {RW.x, RW.y, RW.z, RW.w};
+    float c1[V], c2[V], rwp[V], dP[V], dQ[V];
+    nl_ld<V>(&S.ub[0][ac], c1);
+    nl_ld<V>(&S.ub[1][ac], c2);
+    nl_ld<V>(&S.rw[ac], rwp);
     if (EXACT) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) rwp[i] = rwp[i] > 0.f ? rwp[i] : 1.f;
+        for (int i = 0; i < V; i++) rwp[i] = rwp[i] > 0.f ? rwp[i] : 1.f;
     }
-    float dP[4] = {0.f, 0.f, 0.f, 0.f}, dQ[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < V; i++) dP[i] = dQ[i] = 0.f;
     // exact mode: wt of the own pixel divides 48 quotients per iteration -- its refined reciprocal (the one IEEE
     // division's own fast path computes) is formed once; okp = wt is in the range where that path is exact
-    float rcp_p[4] = {1.f, 1.f, 1.f, 1.f};
-    bool okp[4] = {false, false, false, false};
+    float rcp_p[V];
+    bool okp[V];
+#pragma unroll
+    for (int i = 0; i < V; i++) rcp_p[i] = 1.f, okp[i] = false;
     if (EXACT) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < V; i++) {
             okp[i] = nl_wt_ok(rwp[i]);
             rcp_p[i] = rcp_refined(okp[i] ? rwp[i] : 1.f);
         }
@@ -251,22 +287,21 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
         const int sg = step % NLT_NS;
         mbar_wait(&S.full[sg], (step / NLT_NS) & 1);
         if (act) {
-            const int tc = r * NLT_W + 4 * lane;
-            const float4 W4 = *reinterpret_cast<const float4 *>(&S.own[sg][0][tc]);
-            const float4 P4 = *reinterpret_cast<const float4 *>(&S.own[sg][1][tc]);
-            const float4 Q4 = *reinterpret_cast<const float4 *>(&S.own[sg][2][tc]);
-            const float wv[4] = {W4.x, W4.y, W4.z, W4.w}, po[4] = {P4.x, P4.y, P4.z, P4.w}, qo[4] = {Q4.x, Q4.y, Q4.z, Q4.w};
-            float pr[4], qr[4];
-            nl_shifted4(&S.rec[sg][0][r * NLT_PW + 4 + 4 * lane], l, pr);
-            nl_shifted4(&S.rec[sg][1][r * NLT_PW + 4 + 4 * lane], l, qr);
-            const int nc = ac + k * NLT_PW;  // the quad's column, neighbour row, in the apron tiles
-            float nq1[4], nq2[4], nrw[4];
-            nl_shifted4(&S.ub[0][nc], l, nq1);
-            nl_shifted4(&S.ub[1][nc], l, nq2);
-            nl_shifted4(&S.rw[nc], l, nrw);
-            float pn[4], qn[4];
+            const int tc = r * NLT_W + col0;
+            float wv[V], po[V], qo[V], pr[V], qr[V];
+            nl_ld<V>(&S.own[sg][0][tc], wv);
+            nl_ld<V>(&S.own[sg][1][tc], po);
+            nl_ld<V>(&S.own[sg][2][tc], qo);
+            nl_shifted<V>(&S.rec[sg][0][r * NLT_PW + 4 + col0], l, pr);
+            nl_shifted<V>(&S.rec[sg][1][r * NLT_PW + 4 + col0], l, qr);
+            const int nc = ac + k * NLT_PW;  // the lane's columns, neighbour row, in the apron tiles
+            float nq1[V], nq2[V], nrw[V];
+            nl_shifted<V>(&S.ub[0][nc], l, nq1);
+            nl_shifted<V>(&S.ub[1][nc], l, nq2);
+            nl_shifted<V>(&S.rw[nc], l, nrw);
+            float pn[V], qn[V];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < V; i++) {
                 // wgt holds -2 where the neighbour is outside the frame (nltv_init_kernel) and 0 in the pitch
                 // padding: clamping at 0 makes such a slot contribute nothing and leave its (zero) dual
                 // unchanged, with no per-slot bounds tests.  Everything read for it is finite (zero fill).
@@ -322,8 +357,8 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
                 dP[i] += wm * (pn[i] - Pr);
                 dQ[i] += wm * (qn[i] - Qr);
             }
-            st4(dout + (size_t)s * ks + o, make_float4(pn[0], pn[1], pn[2], pn[3]));
-            st4(dout + (size_t)(NL_SLOTS + s) * ks + o, make_float4(qn[0], qn[1], qn[2], qn[3]));
+            nl_st<V>(dout + (size_t)s * ks + o, pn);
+            nl_st<V>(dout + (size_t)(NL_SLOTS + s) * ks + o, qn);
         }
         if (step + NLT_NS < NL_SLOTS) {
             __syncthreads();  // everyone is done with this stage's buffers
@@ -359,9 +394,9 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
     // ---- primal step (+div) and extrapolation ----
     double esum = 0.0;
     if (act) {
-        float o1[4], o2[4], b1[4], b2[4];
+        float o1[V], o2[V], b1[V], b2[V];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < V; i++) {
             const float dp = EXACT ? dP[i] / rwp[i] : dP[i] * rwp[i], dq = EXACT ? dQ[i] / rwp[i] : dQ[i] * rwp[i];
             o1[i] = u1[i] - tau * (dp + dv1[i]);
             o2[i] = u2[i] - tau * (dq + dv2[i]);
@@ -369,19 +404,19 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
             b1[i] = 2 * o1[i] - u1[i];
             b2[i] = 2 * o2[i] - u2[i];
         }
-        st4(sout + ST_U1 * ks + o, make_float4(o1[0], o1[1], o1[2], o1[3]));
-        st4(sout + ST_U2 * ks + o, make_float4(o2[0], o2[1], o2[2], o2[3]));
-        st4(sout + ST_UB1 * ks + o, make_float4(b1[0], b1[1], b1[2], b1[3]));
-        st4(sout + ST_UB2 * ks + o, make_float4(b2[0], b2[1], b2[2], b2[3]));
+        nl_st<V>(sout + ST_U1 * ks + o, o1);
+        nl_st<V>(sout + ST_U2 * ks + o, o2);
+        nl_st<V>(sout + ST_UB1 * ks + o, b1);
+        nl_st<V>(sout + ST_UB2 * ks + o, b2);
     }
     // printed error only (the exit test is commented out upstream, :1248)
     esum = warp_sum(esum);
-    if (lane == 0) S.red[r] = esum;
+    if (lane == 0) S.red[wi] = esum;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
 #pragma unroll
-        for (int i = 0; i < NLT_H; i++) t += S.red[i];
+        for (int i = 0; i < NLT_WARPS; i++) t += S.red[i];
         atomicAdd(a.err_sum + (size_t)b * a.max_iters + it, t);
     }
 }
