@@ -8,7 +8,7 @@
 
 #include "solver.h"
 #include "tv_kernels.cuh"
-#include "tv_tile_kernel.cuh"
+#include "tma.cuh"
 #include "warp_kernels.cuh"
 #include "nltv_kernels.cuh"
 #include "occ_kernels.cuh"
@@ -304,7 +304,9 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
                 ALLOC(s->csad_t1, B * P);
                 ALLOC(s->csad_t2, B * P);
                 s->csad_perm = (unsigned *)s->dmalloc((size_t)C2_WORDS * B * P);
-                if (!s->csad_perm) return fail(FALDOI_ERR_MEM);
+                const size_t ncta = (size_t)((s->g.pitch + C2_W - 1) / C2_W) * ((h + C2_H - 1) / C2_H);
+                s->csad_partial = (double *)s->dmalloc(2 * (2 * B * ncta));
+                if (!s->csad_perm || !s->csad_partial) return fail(FALDOI_ERR_MEM);
             } else {  // NLTV-CSAD: two-level sorted residual table (csad_select)
                 ALLOC(s->csad_blk, CSAD_FLOATS * B * P);
                 ALLOC(s->csad_sep, CSAD_SEPS * B * P);
@@ -655,11 +657,13 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         const int need = p->max_iters / 2 + 4;
         if (need > s->t2_stride) {
             s->t2_stat = (unsigned char *)s->dmalloc(((size_t)g.B * need + 3) / 4);
-            if (!s->t2_stat) return FALDOI_ERR_MEM;
+            if (csad) s->csad_ticket = (unsigned *)s->dmalloc((size_t)g.B * need);
+            if (!s->t2_stat || (csad && !s->csad_ticket)) return FALDOI_ERR_MEM;
             s->t2_stride = need;
         }
     }
     for (int wp = 0; wp < p->warps; wp++) {
+        if (csad) FALDOI_CUDA(cudaMemsetAsync(s->csad_ticket, 0, (size_t)g.B * s->t2_stride * sizeof(unsigned), s->stream));
         if (csad)
             FALDOI_CUDA(cudaMemsetAsync(s->err_sum, 0, (size_t)g.B * p->max_iters * sizeof(double), s->stream));
         else
@@ -713,7 +717,7 @@ static int run_tv(faldoi_solver *s, const faldoi_params *p, int npairs) {
         const dim3 grid((g.pitch + T2_W - 1) / T2_W, (g.h + T2_H - 1) / T2_H, npairs);
         const dim3 cgrid((g.pitch + C2_W - 1) / C2_W, (g.h + C2_H - 1) / C2_H, npairs);
         const T2Args t2{s->t2_stat, s->t2_stride};
-        const Csad2Args c2{s->csad_perm, s->t2_stat, s->t2_stride};
+        const Csad2Args c2{s->csad_perm, s->t2_stat, s->t2_stride, s->csad_partial, s->csad_ticket};
         for (int c = 0, L = 0; L < nL; c++) {
             if (c >= 2) {
                 FALDOI_CUDA(cudaEventSynchronize(s->chunk_ev[(c - 2) & 3]));

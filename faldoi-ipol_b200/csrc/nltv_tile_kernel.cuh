@@ -21,7 +21,7 @@
 // what changes is who waits for it.
 #pragma once
 #include "nltv_kernels.cuh"
-#include "tv_tile_kernel.cuh"  // tma_box, smem_u32
+#include "tma.cuh"  // tma_box, smem_u32
 
 namespace faldoi {
 
@@ -242,8 +242,7 @@ __global__ void __launch_bounds__(NLT_THREADS, FALDOI_NLT_CTAS) nltv_tile_kernel
                 if (gx0 + i < w && cc[i] != 0.f) {  // 0 marks grad <= GRAD_IS_ZERO (:1734)
                     const float s = (ix[i] * u1[i] + iy[i] * u2[i]) / cc[i];
                     const float med = csad_select(a.blk, a.sep, a.g, b, y, gx0 + i, csad_count(gx0 + i, y, w, h), s, l_t, cc[i]);
-                    v1 = csad_apply(u1[i], ix[i], med, cc[i]);
-                    v2 = csad_apply(u2[i], iy[i], med, cc[i]);
+                    csad_apply2(u1[i], u2[i], ix[i], iy[i], med, cc[i], v1, v2);
                 }
             }
             dv1[i] = div_const(u1[i] - v1, a.dth);

@@ -7,7 +7,7 @@
 
 #include "../../include/faldoi_gpu.h"
 #include "common.cuh"
-#include "tv_tile_kernel.cuh"
+#include "tma.cuh"
 #include "tv_tile2_kernel.cuh"
 #include "tv_csad2_kernel.cuh"
 #include "nltv_tile_kernel.cuh"
@@ -45,11 +45,12 @@ struct faldoi_solver {
     size_t set_stride = 0;
     float *Ix = nullptr, *Iy = nullptr, *rho_c = nullptr, *scale = nullptr, *I1w = nullptr;
     float *csad_blk = nullptr, *csad_sep = nullptr;  // CSAD two-level sorted residual table (csad_select): CSAD_FLOATS per pixel, CSAD_SEPS separator planes
-    faldoi::TileMaps maps{};             // TMA descriptors of the tile kernel (TV family)
     faldoi::Tile2Maps maps2{};           // ... of the two-iteration TVL2 kernel
     faldoi::Csad2Maps cmaps{};           // ... of the two-iteration TV-CSAD kernel
     float *csad_t1 = nullptr, *csad_t2 = nullptr;  // TV-CSAD per-warp constants Ix*u1_0, Iy*u2_0
-    unsigned *csad_perm = nullptr;                 // TV-CSAD: rank-ordered neighbour codes, 12 word planes per pair
+    unsigned *csad_perm = nullptr;                 // TV-CSAD: rank-ordered neighbour codes, 48 bytes per pixel
+    double *csad_partial = nullptr;                // TV-CSAD: per-CTA partial error sums [B][2][CTAs per pair]
+    unsigned *csad_ticket = nullptr;               // TV-CSAD: [B][t2_stride] arrival counters of the ordered sum
     unsigned char *t2_stat = nullptr;    // [B][t2_stride] launch status of the two-iteration kernel
     int t2_stride = 0;
     // NLTV: Lab, weights, duals

@@ -20,9 +20,9 @@
 // stencils, __syncwarp in between).  HBM traffic per pixel and iteration: state 32 B + constants, tiles and
 // codes once per two iterations -- about 95 B against round 1's 228.
 //
-// Exit test (:1543): mean |du|^2 over the frame > tol^2.  The sum is accumulated in double (per-CTA partial sums,
-// one atomicAdd per CTA and iteration) -- the reference's own sum is a racy `err_D +=` inside an OpenMP loop,
-// see DESIGN.md section 2; launch bookkeeping (two iterations per launch, fix-up of an exit after the first) is
+// Exit test (:1543): mean |du|^2 over the frame > tol^2.  The sum is accumulated in double, deterministically
+// (per-CTA partial sums added up in a fixed order by the last CTA to finish) -- the reference's own sum is a racy
+// `err_D +=` inside an OpenMP loop; launch bookkeeping (two iterations per launch, fix-up of an exit after the first) is
 // tv_tile2_kernel's with the mean in place of the maximum.
 #pragma once
 #include "tv_tile2_kernel.cuh"
@@ -60,6 +60,7 @@ struct Csad2Smem {
     float i0_[C2_T_FLOATS], iw_[C2_T_FLOATS];
     double red[2][C2_WARPS];
     unsigned long long bar;
+    int last;
     __device__ __forceinline__ float *ub(int k, int r) { return &ub_[k][(r + 2) * C2_PW]; }
     __device__ __forceinline__ float *xi(int k, int r) { return &xi_[k][(r + 2) * C2_PW]; }
     __device__ __forceinline__ float *pl(int k, int r) { return &pl_[k][(r + 1) * C2_PW]; }
@@ -76,6 +77,10 @@ struct Csad2Args {
     const unsigned *perm;  // [B][plane][C2_WORDS]: the 48 code bytes of a pixel, contiguous, byte r = the code of rank r
     unsigned char *stat;   // [B][stat_stride]: 1 = that launch ran both iterations normally
     int stat_stride;
+    // deterministic error sums: every CTA stores its two partial sums, the last CTA of a pair to finish (ticket
+    // counter) adds them up in a fixed order -- the value that feeds the exit test does not depend on scheduling
+    double *partial;   // [B][2][CTAs per pair]
+    unsigned *ticket;  // [B][stat_stride]
 };
 
 // neighbour code of window offset (dy, dx), dy, dx in -3..3: one byte, decoded with a shift and a mask
@@ -315,15 +320,9 @@ __device__ __forceinline__ void c2_dual_quad(Csad2Smem &S, int r, int qi, int gx
         x12[k] = x12[k] + tau * u1y;
         x21[k] = x21[k] + tau * u2x;
         x22[k] = x22[k] + tau * u2y;
-        // divide by max(1, |xi_old|): x / 1 == x, so only saturated rows divide
-        if (nr1 > 1.f) {
-            x11[k] /= nr1;
-            x12[k] /= nr1;
-        }
-        if (nr2 > 1.f) {
-            x21[k] /= nr2;
-            x22[k] /= nr2;
-        }
+        // divide by max(1, |xi_old|): x / 1 == x, so only saturated rows divide (two quotients, one reciprocal)
+        if (nr1 > 1.f) div2_shared(x11[k], x12[k], nr1);
+        if (nr2 > 1.f) div2_shared(x21[k], x22[k], nr2);
     }
     *reinterpret_cast<float4 *>(S.xi(0, r) + cx) = make_float4(x11[0], x11[1], x11[2], x11[3]);
     *reinterpret_cast<float4 *>(S.xi(1, r) + cx) = make_float4(x12[0], x12[1], x12[2], x12[3]);
@@ -371,10 +370,7 @@ __device__ __forceinline__ double c2_primal_quad(Csad2Smem &S, const TvArgs &a, 
         }
         float v1 = u1[k], v2 = u2[k];
         const bool in = (gx >= 0 && gx < w);
-        if (in) {
-            v1 = csad_apply(u1[k], ix[k], md[k], sc[k]);
-            v2 = csad_apply(u2[k], iy[k], md[k], sc[k]);
-        }
+        if (in) csad_apply2(u1[k], u2[k], ix[k], iy[k], md[k], sc[k], v1, v2);
         // u - v is exactly 0 wherever the data term keeps u (a third of the pixels): 0 / theta = 0, and IEEE division
         // would send that lane -- and its warp -- through the out-of-line slow path
         const float x1 = u1[k] - v1, x2 = u2[k] - v2;
@@ -530,6 +526,37 @@ __global__ void __launch_bounds__(C2_THREADS, FALDOI_C2_CTAS) tv_csad2_kernel(co
         S.red[1][wi] = esumB;
     }
     __syncthreads();
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    double *pp = c2.partial + (size_t)b * 2 * ncta;
+    if (tid == 0) {
+        double sA = 0.0, sB = 0.0;
+        for (int i = 0; i < C2_WARPS; i++) {
+            sA += S.red[0][i];
+            sB += S.red[1][i];
+        }
+        pp[cta] = sA;
+        pp[ncta + cta] = sB;
+        __threadfence();
+        S.last = (atomicAdd(c2.ticket + (size_t)b * c2.stat_stride + L, 1u) == (unsigned)(ncta - 1));
+    }
+    __syncthreads();
+    if (!S.last) return;
+    // the last CTA of this pair: ordered sum of all partial sums (fixed assignment of CTAs to threads, fixed
+    // shuffle tree, warps added in order)
+    __threadfence();
+    double tA = 0.0, tB = 0.0;
+    for (int i = tid; i < ncta; i += C2_THREADS) {
+        tA += __ldcg(pp + i);
+        tB += __ldcg(pp + ncta + i);
+    }
+    tA = warp_sum(tA);
+    tB = warp_sum(tB);
+    __syncthreads();
+    if (lane == 0) {
+        S.red[0][wi] = tA;
+        S.red[1][wi] = tB;
+    }
+    __syncthreads();
     if (tid == 0) {
         double sA = 0.0, sB = 0.0;
         for (int i = 0; i < C2_WARPS; i++) {
@@ -538,10 +565,10 @@ __global__ void __launch_bounds__(C2_THREADS, FALDOI_C2_CTAS) tv_csad2_kernel(co
         }
         double *e = a.err_sum + (size_t)b * a.max_iters + it;
         if (mode == T2_MODE_TWO) {
-            atomicAdd(e, sA);
-            atomicAdd(e + 1, sB);
+            e[0] = sA;
+            e[1] = sB;
         } else {
-            atomicAdd(e, sB);
+            e[0] = sB;
         }
     }
 }

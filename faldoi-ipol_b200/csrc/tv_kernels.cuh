@@ -150,22 +150,34 @@ __device__ __forceinline__ float csad_select(const float *__restrict__ blk, cons
     return csad_finish(csad_gather(blk, g, b, y, x, j), j, np, s, l_t, scale);
 }
 
-// u - g*med/scale of the CSAD data term.  med is exactly 0 whenever the rank lands on the middle threshold
-// (t_{n/2} = 0: "keep u"), which is common; (g*0)/scale is the signed zero g*0 itself, and IEEE division
-// would send that zero numerator through its out-of-line slow path (30 % of the divisions of the tile
-// kernel, 14 % of its instructions) -- so those lanes skip the division.  Same bits.
-__device__ __forceinline__ float csad_apply(float u, float g, float med, float scale) {
-    const float n = g * med;
-    if (n == 0.f) return u - n;
-    return u - n / scale;
+// v = u - (Ix, Iy) * med / scale of the CSAD data term (:1570, :1757).  med is exactly 0 whenever the rank lands on
+// the middle threshold (t_{n/2} = 0: "keep u"), which is common -- a third of the pixels -- and a zero numerator
+// sends IEEE division, and with it the whole warp, through its out-of-line slow path (the compiler turns an
+// `if (n == 0)` around the division into a select, so the division still executes).  The two quotients share the
+// refined reciprocal of scale instead (common.cuh: rcp_refined / div_by_rcp), which has no such path: 0 / scale
+// is the signed zero itself, everything else is bit for bit the IEEE quotient; out-of-range operands take `/`.
+__device__ __forceinline__ void csad_apply2(float u1, float u2, float ix, float iy, float med, float scale, float &v1, float &v2) {
+    const float n1 = ix * med, n2 = iy * med;
+    float q1, q2;
+    if (scale >= 7.450580596923828e-09f && scale < 1048576.f && fastdiv_num_ok(n1) && fastdiv_num_ok(n2)) {
+        const float rs = rcp_refined(scale);
+        q1 = div_by_rcp(n1, scale, rs);
+        q2 = div_by_rcp(n2, scale, rs);
+    } else {
+        q1 = n1 / scale;
+        q2 = n2 / scale;
+    }
+    v1 = u1 - (n1 == 0.f ? n1 : q1);
+    v2 = u2 - (n2 == 0.f ? n2 : q2);
 }
 
 // Norm used by TV-CSAD's row-wise projection, max(1, hypotf(a,b)) (tvcsad_getD :1433-1443).
-// Only values > 1 matter; a^2+b^2 evaluated in fp32 is within 3 ulp of the exact sum, so
-// below 0.999 the exact hypot is certainly <= 1 and the double-precision path is skipped.
+// Only values > 1 matter; a^2+b^2 evaluated in fp32 is within 1.5 ulp (1.8e-7 relative) of the exact sum, so
+// below 1 - 5e-7 the exact sum is below 1 - 3e-7, its square root -- however glibc rounds it -- is below 1,
+// and the double-precision path is skipped.
 __device__ __forceinline__ float proj_norm_hypot(float a, float b) {
     const float s = a * a + b * b;
-    if (s < 0.999f) return 1.f;
+    if (s < 0.9999995f) return 1.f;
     return hypotf_exact(a, b);
 }
 

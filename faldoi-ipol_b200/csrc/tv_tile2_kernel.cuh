@@ -18,7 +18,7 @@
 // iterating, redoes that single iteration from set P into set P^1 ("fix-up", no error update).
 // stat[b][L] records whether launch L ran normally, so every launch decides from O(1) words.
 #pragma once
-#include "tv_tile_kernel.cuh"
+#include "tma.cuh"
 
 namespace faldoi {
 
