@@ -236,6 +236,11 @@ __device__ __forceinline__ float t2_primal_quad(Tile2Smem &S, const TvArgs &a, i
 struct T2Args {
     unsigned char *stat;  // [B][max_iters/2 + 2]: 1 = that launch ran both iterations normally
     int stat_stride;
+    // Row-stripe mode (stripes.inc), all zero otherwise:
+    int force;          // 0: decide from the error history; T2_MODE_TWO / T2_MODE_ONE: run exactly that, no bookkeeping
+    int boundary_first; // CTAs of the tile rows next to a stripe boundary come first in the launch order
+    unsigned *sig_cnt;  // [2] arrival counters of the boundary CTAs (towards the upper / lower neighbour)
+    unsigned *sig_up, *sig_dn;  // flag words in the neighbour GPUs' memory: "my boundary rows of launch n are in your halo"
 };
 
 __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
@@ -246,10 +251,18 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
     const int par0 = a.parity[b];
     const int it = 2 * L;  // first iteration of this launch
+    // tile row of this CTA.  Stripe mode: the CTAs that produce a neighbour's halo rows (tile row 0; the last two tile
+    // rows) are dispatched first, so that their rows -- and the signal that they are there -- cross NVLink while the
+    // interior of the stripe is still being computed.
+    const int nby = gridDim.y;
+    int by = blockIdx.y;
+    if (t2.boundary_first && nby >= 3) by = (by == 0) ? 0 : (by <= 2 ? nby - 3 + by : by - 2);
 
     // ---- what does this launch do for pair b?  (see the header comment) ----
     int mode, par_in = (par0 + L) & 1;
-    {
+    if (t2.force) {
+        mode = t2.force;
+    } else {
         unsigned char *st = t2.stat + (size_t)b * t2.stat_stride;
         if (L == 0) {
             mode = (it + 1 < a.max_iters) ? T2_MODE_TWO : T2_MODE_ONE;
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
     if (mode == T2_MODE_SKIP) return;
 
     const int w = a.g.w, h = a.g.h, pitch = a.g.pitch, hg = a.g.hg, yo = a.g.y_off;
-    const int x0 = blockIdx.x * T2_W, y0 = blockIdx.y * T2_H;
+    const int x0 = blockIdx.x * T2_W, y0 = by * T2_H;
     const int rows = min(T2_H, h - y0);
     const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
     float *out = a.state + (size_t)(par_in ^ 1) * a.set_stride + (size_t)b * plane;
@@ -381,6 +394,32 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
                 st4(po + ST_U2 * pp, make_float4(o2[0], o2[1], o2[2], o2[3]));
                 st4(po + ST_UB1 * pp, make_float4(ob1[0], ob1[1], ob1[2], ob1[3]));
                 st4(po + ST_UB2 * pp, make_float4(ob2[0], ob2[1], ob2[2], ob2[3]));
+            }
+        }
+    }
+
+    // ---- stripe mode: tell the neighbour GPU that this launch's boundary rows are in its halo ----
+    // Every boundary CTA has stored its rows through the peer mapping; the last one to arrive (counter in local
+    // memory) publishes the launch number with a system-scope release store into the neighbour's flag word, on
+    // which the neighbour's next launch waits (stream memory operation) -- no host, no all-to-all.
+    if (t2.boundary_first && (by == 0 || by >= nby - 2)) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            if (by == 0 && t2.sig_up) {
+                const unsigned n = atomicAdd(&t2.sig_cnt[0], 1u) + 1u;
+                if (n % gridDim.x == 0) {
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(t2.sig_up), "r"(n / gridDim.x) : "memory");
+                }
+            }
+            if (by >= nby - 2 && t2.sig_dn) {
+                const unsigned n = atomicAdd(&t2.sig_cnt[1], 1u) + 1u;
+                const unsigned per_launch = min(2, nby) * gridDim.x;
+                if (n % per_launch == 0) {
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(t2.sig_dn), "r"(n / per_launch) : "memory");
+                }
             }
         }
     }

@@ -13,6 +13,7 @@
 //                    a sequence is sharded by pair, one host thread + batched handle per GPU
 //   -stripes 0       never cut a frame into stripes
 //   -seq_stats 1     per GPU, where the host thread of a sequence spent its time (stderr)
+//   -pinned 0|1      sequence staging buffers in ordinary / page-locked memory (default: page-locked for long sequences)
 //   -host_preproc 1  run main()'s preprocessing on the host instead of the GPU
 //   -seq jobs.txt    many pairs in one process (one job per line: the positional arguments of a normal call).
 //                    Files are read and decoded by a pool of host threads, jobs of equal size fill the slots of a
@@ -21,8 +22,10 @@
 //                    one process per pair (scripts_python/faldoi_sift.py:314-318)
 // There is no CPU fallback: without a usable GPU the program reports the error and fails.
 #include <malloc.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -99,7 +102,7 @@ bool is_nltv(int m) {
 }
 
 struct Options {
-    int val_method = 0, nwarps = 5, glb_it = 400, device = 0, batch = 16;
+    int val_method = 0, nwarps = 5, glb_it = 400, device = 0, batch = 16, pinned = -1;
     bool verbose = false, host_preproc = false, stripes = true, seq_stats = false;
     std::vector<int> devices;
     std::string file_params;
@@ -111,7 +114,57 @@ struct Slot {
     float *pin = nullptr;
     size_t cap = 0;  // floats
 };
-bool g_pinned_staging = true;  // false when no CUDA device is visible (page-locking needs the driver)
+
+// Staging memory for the slots, carved out of a few large arenas that live as long as the sequence (slots are
+// reused from job to job, so no job pays for fresh pages).  Page-locked arenas make the copies to and from the GPU
+// asynchronous and faster, but page-locking is slow -- measured on the B200 hosts: 40 ms per 22 MB slot, and
+// concurrent cudaHostAlloc calls serialise inside the driver -- against ~2 ms per pair for staged copies from
+// ordinary memory; it pays off once every slot has been reused some twenty times.  Hence: page-locked for long
+// sequences (or -pinned 1), ordinary memory otherwise (or -pinned 0); one thread allocates at a time, a few slots
+// per call, and only as the pipeline actually fills.
+class PinnedArenas {
+  public:
+    PinnedArenas(size_t slots_per_arena, bool pinned) : per_arena_(slots_per_arena ? slots_per_arena : 1), pinned_(pinned) {}
+    ~PinnedArenas() {
+        for (float *a : arenas_) pinned_ ? faldoi_pinned_free(a) : free(a);
+    }
+    // memory for one slot of `need` floats (nullptr on failure: the job then decodes into its own vectors)
+    float *carve(size_t need) {
+        std::lock_guard<std::mutex> l(mu_);
+        if (need != slot_floats_ || left_ == 0) {
+            float *a = nullptr;
+            if (pinned_) {
+                a = (float *)faldoi_pinned_alloc(need * per_arena_ * sizeof(float));
+            } else if (posix_memalign((void **)&a, 4096, need * per_arena_ * sizeof(float)) != 0) {
+                a = nullptr;
+            }
+            if (!a) return nullptr;
+            arenas_.push_back(a);
+            cur_ = a, slot_floats_ = need, left_ = per_arena_;
+        }
+        float *p = cur_;
+        cur_ += need;
+        left_--;
+        return p;
+    }
+
+  private:
+    std::mutex mu_;
+    std::vector<float *> arenas_;
+    float *cur_ = nullptr;
+    size_t per_arena_, slot_floats_ = 0, left_ = 0;
+    bool pinned_;
+};
+PinnedArenas *g_arenas = nullptr;
+bool g_have_gpu = true;  // false when no CUDA device is visible (page-locking needs the driver)
+// -seq_stats 1: where the host side of a sequence spends its time (microseconds, summed over all threads)
+std::atomic<long long> g_us_pin{0}, g_us_decode{0}, g_us_save{0}, g_us_prepare{0}, g_us_wait_load{0};
+struct UsTimer {
+    std::atomic<long long> &acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit UsTimer(std::atomic<long long> &a) : acc(a) {}
+    ~UsTimer() { acc += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 // Stage 1 of a job (host I/O, no messages): ims.txt + the frames, the flow and the occlusion
 // mask.  A single call decodes its files concurrently; a sequence decodes many jobs at once
@@ -141,14 +194,14 @@ Loaded load_inputs(const std::vector<std::string> &args, int val_method, bool pa
         const bool third_is_i1 = (third == filename_i1);  // the same file: decode it once
         // staging layout from the first frame's header: three frames of pd planes, the flow (2), the mask (1)
         faldoi_host::Sink s0, s1, s2, sf, so;
-        if (slot && g_pinned_staging) {
+        if (slot) {
             try {
                 int w = 0, h = 0, pd = 0;
                 faldoi_host::probe_image(filename_i0, &w, &h, &pd);
                 const size_t n = (size_t)w * h, need = (3 * (size_t)pd + 3) * n;
-                if (need > slot->cap) {
-                    faldoi_pinned_free(slot->pin);
-                    slot->pin = (float *)faldoi_pinned_alloc(need * sizeof(float));
+                if (need > slot->cap && g_arenas) {
+                    UsTimer tp(g_us_pin);
+                    slot->pin = g_arenas->carve(need);
                     slot->cap = slot->pin ? need : 0;
                 }
                 if (slot->pin) {
@@ -159,6 +212,7 @@ Loaded load_inputs(const std::vector<std::string> &args, int val_method, bool pa
             } catch (...) {  // the real read below reports what is wrong with the file
             }
         }
+        UsTimer td(g_us_decode);
         auto rd = [](std::string f, faldoi_host::Sink s) { return faldoi_host::read_image_split(f, s); };
         const auto policy = parallel ? std::launch::async : std::launch::deferred;
         std::future<Image> f0 = std::async(policy, rd, filename_i0, s0);
@@ -290,6 +344,7 @@ void report_job(const Ready &R, bool verbose) {
 
 // Stage 3 of a job: the output files.
 void save_job(const Ready &R) {
+    UsTimer ts(g_us_save);
     faldoi_host::write_image_float_split(R.flow_file, R.u, R.w, R.h, 2);
     if (R.method == FALDOI_M_TVL1_OCC && !R.passthrough) {
         std::vector<int> occ((size_t)R.w * R.h);
@@ -402,9 +457,6 @@ class SlotPool {
   public:
     explicit SlotPool(size_t n) : slots_(n) {
         for (size_t i = 0; i < n; i++) free_.push_back((int)i);
-    }
-    ~SlotPool() {
-        for (Slot &s : slots_) faldoi_pinned_free(s.pin);
     }
     int try_acquire() {
         std::lock_guard<std::mutex> l(mu_);
@@ -633,13 +685,18 @@ int run_sequence(const std::string &seq_file, const std::string &argv0, const Op
         joblist.push_back(job);
     }
     const size_t njobs = joblist.size(), ndev = opt.devices.size();
-    // per GPU: one batch on the device, one queued, one being assembled and one on its way to disk
-    SlotPool slots(std::max<size_t>(4 * (size_t)opt.batch * ndev, 8));
+    // per GPU: one batch on the device, one queued or being assembled, one on its way to disk
+    const size_t nslots = std::max<size_t>(3 * (size_t)opt.batch * ndev, 8);
+    const bool pinned = g_have_gpu && (opt.pinned == 1 || (opt.pinned < 0 && njobs >= 20 * nslots));
+    PinnedArenas arenas(4, pinned);
+    g_arenas = &arenas;
+    SlotPool slots(nslots);
     const size_t window = std::max<size_t>(2 * (size_t)opt.batch * ndev, 4);
     ThreadPool io(std::max(4u, std::min(64u, std::thread::hardware_concurrency())));
     int rc = EXIT_SUCCESS;
     int done = 0;
     std::string err;
+    const auto t_seq0 = std::chrono::steady_clock::now();
     {
         std::vector<std::unique_ptr<DeviceWorker>> workers;
         for (int d : opt.devices) workers.emplace_back(new DeviceWorker(d, opt, io, slots));
@@ -689,12 +746,17 @@ int run_sequence(const std::string &seq_file, const std::string &argv0, const Op
                 flush();
                 start_load(slots.acquire());
             }
-            Loaded in = loading.front().fut.get();
+            Loaded in;
+            {
+                UsTimer tw(g_us_wait_load);
+                in = loading.front().fut.get();
+            }
             const int slot = loading.front().slot;
             loading.pop_front();
             std::unique_ptr<Ready> R(new Ready());
             R->slot = slot;
             try {
+                UsTimer tp(g_us_prepare);
                 std::lock_guard<std::mutex> l(g_io_mu);
                 const int r = prepare_job(joblist[k], opt, std::move(in), *R);
                 if (r != EXIT_SUCCESS) rc = r;
@@ -724,6 +786,14 @@ int run_sequence(const std::string &seq_file, const std::string &argv0, const Op
             if (err.empty()) err = w->error();
         }
     }
+    if (opt.seq_stats) {
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_seq0).count();
+        fprintf(stderr, "pipeline: %d pairs in %.3f s = %.1f pairs/s, files in to files out (handle creation included, process and CUDA start-up not)\n",
+                done, secs, done / secs);
+    }
+    if (opt.seq_stats)
+        fprintf(stderr, "host: dispatcher waited for decoded jobs %.3f s, checks %.3f s; summed over the I/O threads: decode %.3f s, page-locking %.3f s, "
+                        "writing %.3f s\n", g_us_wait_load / 1e6, g_us_prepare / 1e6, g_us_decode / 1e6, g_us_pin / 1e6, g_us_save / 1e6);
     if (!err.empty()) {
         fprintf(stderr, "ERROR: %s\n", err.c_str());
         return EXIT_FAILURE;
@@ -753,6 +823,7 @@ int main(int argc, char *argv[]) {
     const bool host_preproc = pick_option(args, "host_preproc", "0") == "1";
     const bool stripes = pick_option(args, "stripes", "1") != "0";
     const bool seq_stats = pick_option(args, "seq_stats", "0") == "1";
+    const std::string pinned_str = pick_option(args, "pinned", "-1");
     const std::string seq_file = pick_option(args, "seq", "");
 
     if (seq_file.empty() && args.size() != 6 && args.size() != 4) {
@@ -767,12 +838,13 @@ int main(int argc, char *argv[]) {
         opt.glb_it = std::stoi(global_iters);
         opt.device = device_str.empty() ? 0 : std::stoi(device_str);
         opt.batch = std::max(1, std::stoi(batch_str));
+        opt.pinned = std::stoi(pinned_str);
         if (verbose_str != "0" && verbose_str != "1") throw std::invalid_argument("-verbose takes 0 or 1");
         opt.verbose = (verbose_str == "1");
         // GPUs: -devices list | "all"; else -device d; else device 0.  A single call without either option may
         // use every visible GPU (row stripes of a >= 4K frame).
         const int visible = faldoi_device_count();
-        g_pinned_staging = visible > 0;
+        g_have_gpu = visible > 0;
         if (devices_str == "all" || (devices_str.empty() && device_str.empty() && seq_file.empty())) {
             for (int d = 0; d < visible; d++) opt.devices.push_back(d);
         } else if (!devices_str.empty()) {

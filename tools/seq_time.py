@@ -58,7 +58,7 @@ def main():
             res[jobs] = time.perf_counter() - t0
             assert r.returncode == 0 and ("sequence: %d pairs done" % jobs) in r.stderr, r.stderr[-2000:]
             print("%d pairs on devices %s, batch %s: %.2f s wall" % (jobs, devices, batch, res[jobs]), flush=True)
-            print("".join(m + "\n" for m in re.findall(r"device \d+: waiting[^\n]*", r.stderr)), end="")
+            print("".join(m + "\n" for m in re.findall(r"(?:device \d+: waiting|host: dispatcher|pipeline: )[^\n]*", r.stderr)), end="")
         if n > 4:
             dt = res[n] - res[min(4, n)]
             print("marginal: %.4f s per pair = %.1f pairs/s (start-up + first 4 pairs: %.2f s)" % (dt / (n - 4), (n - 4) / dt, res[4]))
