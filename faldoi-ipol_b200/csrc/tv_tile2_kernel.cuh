@@ -241,6 +241,8 @@ struct T2Args {
     int boundary_first; // CTAs of the tile rows next to a stripe boundary come first in the launch order
     unsigned *sig_cnt;  // [2] arrival counters of the boundary CTAs (towards the upper / lower neighbour)
     unsigned *sig_up, *sig_dn;  // flag words in the neighbour GPUs' memory: "my boundary rows of launch n are in your halo"
+    const unsigned *wait_up, *wait_dn;  // the flag words the neighbours write in THIS GPU's memory
+    unsigned wait_val;                  // launches every stripe has been asked to complete before this one
 };
 
 __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
@@ -291,6 +293,23 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
     float *out = a.state + (size_t)(par_in ^ 1) * a.set_stride + (size_t)b * plane;
 
     if (tid == 0) {
+        // Stripe mode: a CTA next to a stripe boundary reads halo rows the neighbour GPU stores, and overwrites halo
+        // rows the neighbour reads.  Both are safe once the neighbour's boundary CTAs of the launch before have
+        // finished, which they announce in a flag word in this GPU's memory: poll it (acquire, system scope) before
+        // the tile is loaded.  Interior CTAs -- and the stream -- never wait, so the launches stay back to back.
+        if (t2.boundary_first) {
+            const unsigned *f = (by == 0) ? t2.wait_up : (by >= nby - 2 ? t2.wait_dn : nullptr);
+            const unsigned *f2 = (by == 0 && by >= nby - 2) ? t2.wait_dn : nullptr;  // a stripe of one or two tile rows
+            for (int k = 0; k < 2; k++) {
+                const unsigned *q = k ? f2 : f;
+                if (!q) continue;
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(q) : "memory");
+                } while (v < t2.wait_val);
+            }
+            asm volatile("fence.proxy.async;\n" ::: "memory");  // the TMA loads below must see what the flag announced
+        }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"((unsigned)T2_TX_BYTES) : "memory");
