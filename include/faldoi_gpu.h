@@ -49,7 +49,13 @@ typedef struct faldoi_params {
     float lambda, theta, tau, beta, alpha, tau_u, tau_eta, tau_chi, mu, tol;
 } faldoi_params;
 
-/* What `-verbose 1` prints per warp ("Warping: k,Iter: n Error: e"). */
+/* What `-verbose 1` prints per warp ("Warping: k,Iter: n Error: e").
+ * Iteration counts equal the reference's.  For TVL2 and TVL2-OCC the exit test is an exact maximum, so the
+ * counts are bit-determined.  For TV-CSAD the test is mean |du|^2 > tol^2 (src/global_faldoi.cpp:1543): the sum is
+ * taken over all pixels in double precision in a fixed order (deterministic run to run), whereas the reference
+ * adds in fp32 in pixel order -- under OpenMP with a data race -- so an error within a few
+ * ulp of tol^2 could leave the loop one iteration apart from a single-threaded reference run; the printed errors
+ * of the CSAD / NLTV models agree to ~1e-6 relative, not bit for bit. */
 typedef struct faldoi_log {
     int iters[FALDOI_MAX_WARPS];
     float err[FALDOI_MAX_WARPS];
@@ -183,12 +189,14 @@ int faldoi_guided_tvl2coupled_occ(const float *I0, const float *I1, const float 
 
 /* ---- row stripes: ONE large frame pair over several GPUs (>= 4K frames) ------------
  * The frame is cut into `nstripes` contiguous row blocks, stripe k on CUDA device
- * devices[k] (devices may repeat, e.g. to exercise the path on one GPU).  Every fused
- * iteration stores the rows next to a stripe boundary directly into the neighbour GPU's
- * halo rows over NVLink peer mappings; the exit test uses the maximum over the whole
- * frame, so results (flow, per-warp iteration counts) are identical to the single-GPU
- * solve.  Implemented for TVL2 (methods 0,1).  The reference has no counterpart: its
- * tvl2OF (src/global_faldoi.cpp:556) is single-node OpenMP. */
+ * devices[k] (devices may repeat, e.g. to exercise the path on one GPU).  Every launch of the
+ * iteration kernel stores the rows next to a stripe boundary directly into the neighbour GPU's
+ * halo rows over NVLink peer mappings and signals it through a flag word in its memory; the exit
+ * test uses the maximum over the whole frame (gathered once per block of launches, with a
+ * checkpoint to roll back to), so results (flow, per-warp iteration counts, errors) are identical
+ * to the single-GPU solve.  Needs peer access between the devices and stream memory operations.
+ * Implemented for TVL2 (methods 0,1).  The reference has no counterpart: its tvl2OF
+ * (src/global_faldoi.cpp:556) is single-node OpenMP. */
 typedef struct faldoi_stripes faldoi_stripes;
 int faldoi_stripe_rows(int h, int nstripes, int k, int *row0, int *row1); /* rows [row0,row1) owned by stripe k */
 int faldoi_stripes_create(faldoi_stripes **out, int nstripes, const int *devices, int w, int h, int method);
