@@ -346,3 +346,75 @@ def test_cli_sequence_pipeline_occ_and_errors(H, tmp_path, po):
     assert r.returncode != 0 and "ERROR" in r.stderr
     assert np.array_equal(po.read_flo(str(tmp_path / "p0.flo")), g["u_m8_w1_i12"])
     assert not os.path.exists(tmp_path / "p1.flo") and not os.path.exists(tmp_path / "p2.flo")
+
+
+def test_cli_sequence_pipeline_without_gpu(H, tmp_path, po):
+    """The host side of -seq (decode pool, staging slots, batching by size, writer pool, stop at the first failing
+    job) exercised without a GPU: method id -1 makes every job a pass-through (the reference writes the input flow
+    back for ids outside 0..8), so results are known and no solver is needed."""
+    ga, gb = load_case("crop_a"), load_case("crop_b")
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    ims_a, flo_a = _write_case(tmp_path / "a", ga, po)
+    ims_b, flo_b = _write_case(tmp_path / "b", gb, po)
+    order = "aabbbabab" * 3
+    outs = [str(tmp_path / ("o%02d.flo" % k)) for k in range(len(order))]
+    (tmp_path / "jobs.txt").write_text("".join("%s %s %s\n" % ((ims_a, flo_a, o) if c == "a" else (ims_b, flo_b, o))
+                                               for c, o in zip(order, outs)))
+    r = subprocess.run([BIN, "-seq", str(tmp_path / "jobs.txt"), "-m", "-1", "-batch", "3", "-seq_stats", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "sequence: %d pairs done" % len(order) in r.stderr and "pipeline: %d pairs" % len(order) in r.stderr
+    for c, o in zip(order, outs):
+        assert open(o, "rb").read() == open(flo_a if c == "a" else flo_b, "rb").read()
+    # a job in the middle whose flow file is missing: non-zero exit, earlier jobs complete, later jobs not started
+    lines = (tmp_path / "jobs.txt").read_text().splitlines()
+    for o in outs:
+        os.remove(o)
+    lines[7] = "%s %s %s" % (ims_a, tmp_path / "nope.flo", outs[7])
+    (tmp_path / "bad.txt").write_text("\n".join(lines) + "\n")
+    r = subprocess.run([BIN, "-seq", str(tmp_path / "bad.txt"), "-m", "-1", "-batch", "3"], capture_output=True, text=True)
+    assert r.returncode != 0 and "ERROR" in r.stderr
+    assert all(os.path.exists(o) for o in outs[:7]) and not any(os.path.exists(o) for o in outs[7:])
+    # a job line with the wrong number of file names is refused before anything runs
+    (tmp_path / "short.txt").write_text("%s %s\n" % (ims_a, flo_a))
+    r = subprocess.run([BIN, "-seq", str(tmp_path / "short.txt"), "-m", "-1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "needs 3 or 5 file names" in r.stderr
+
+
+def test_png_header_is_validated(H, tmp_path):
+    """Untrusted PNG headers: bit depths the specification does not allow for the colour type and absurd sizes are
+    refused before any allocation or shift uses them."""
+    import struct
+    import zlib
+
+    def png(w, h, depth, ctype, payload=b"\0" * 16):
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+        return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(payload)) + chunk(b"IEND", b""))
+
+    for name, data, msg in (("depth0.png", png(4, 4, 0, 0), "bit depth"), ("depth32.png", png(4, 4, 32, 2), "bit depth"),
+                            ("rgb4.png", png(4, 4, 4, 2), "bit depth"), ("huge.png", png(0x7fffffff, 0x7fffffff, 8, 0), "too large")):
+        path = tmp_path / name
+        path.write_bytes(data)
+        with pytest.raises(RuntimeError) as e:
+            _read(H, str(path))
+        assert msg in str(e.value)
+    # a valid 2x1 gray image still decodes
+    ok = tmp_path / "ok.png"
+    ok.write_bytes(png(2, 1, 8, 0, b"\0\x07\x09"))
+    a = _read(H, str(ok))
+    assert a.shape == (1, 1, 2) and a[0, 0, 0] == 7 and a[0, 0, 1] == 9
+
+
+def test_write_errors_are_reported(H, tmp_path, po):
+    """A full disk (/dev/full) while writing the flow must end in an error, not in a truncated file behind a successful exit."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full here")
+    u = np.zeros((2, 64, 64), np.float32)
+    assert H.faldoi_host_write_flo(b"/dev/full", _p(u[0]), _p(u[1]), 64, 64) != 0
+    assert b"writing" in H.faldoi_host_last_error()
+    g = load_case("crop_b")
+    ims, flo = _write_case(tmp_path, g, po)
+    r = subprocess.run([BIN, ims, flo, "/dev/full", "-m", "-1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "ERROR" in r.stderr

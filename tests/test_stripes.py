@@ -120,3 +120,22 @@ def test_striped_across_gpus(fb, sync, monkeypatch):
     assert list(log.iters[:2]) == its
     assert np.array_equal(u, whole)
     g.close()
+
+
+def test_reference_arm_under_torchrun_uses_all_cores(po):
+    """bench.py --impl reference launched the way the driver launches it for N > 1: torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers; rank 0 must pin the reference's OpenMP team back to every host core and be the
+    only rank that prints a line (round 1's N>1 reference arm ran single-threaded: ratios inflated 2.9x)."""
+    import json
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29543", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--width", "256", "--height", "128"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["omp_num_threads"] == os.cpu_count() and d["cpu_baseline"]["cores"] == os.cpu_count()
+    assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
