@@ -46,7 +46,6 @@ sys.path.insert(0, ROOT)
 ALG_BYTES = {0: 80, 1: 80, 4: 84, 5: 84, 2: 532, 3: 532, 6: 536, 7: 536, 8: 2370}  # SURVEY.md 8(d), per px*iter
 KERNEL = {0: "tv_tile2_kernel", 1: "tv_tile2_kernel", 4: "tv_csad2_kernel", 5: "tv_csad2_kernel", 2: "nltv_tile_kernel",
           3: "nltv_tile_kernel", 6: "nltv_tile_kernel<CSAD>", 7: "nltv_tile_kernel<CSAD>", 8: "occ_xi_rows_kernel + occ_chi_rows_kernel"}
-NAMES = {0: "tvl2", 4: "tvcsad", 7: "nltvcsad_w", 8: "tvl2_occ", 2: "nltv", 6: "nltvcsad"}
 
 
 def parse():
