@@ -100,7 +100,9 @@ __device__ __forceinline__ void t2_dual_quad(Tile2Smem &S, int r, int qi, int gx
         const float u2x = (full || gx0 + k < w - 1) ? b2[k + 1] - b2[k] : 0.f;
         const float u1y = ylast ? 0.f : n1[k] - b1[k];
         const float u2y = ylast ? 0.f : n2[k] - b2[k];
-        nr[k] = sqrtf(x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k]);
+        // |xi_old|^2; the square root is only taken where it matters: sqrtf(s) > 1 implies s > 1, and where s > 1 but
+        // sqrtf(s) rounds to 1 the division below is by exactly 1
+        nr[k] = x11[k] * x11[k] + x12[k] * x12[k] + x21[k] * x21[k] + x22[k] * x22[k];
         big = fmaxf(big, nr[k]);
         x11[k] = x11[k] + tau * u1x;
         x12[k] = x12[k] + tau * u1y;
@@ -111,7 +113,9 @@ __device__ __forceinline__ void t2_dual_quad(Tile2Smem &S, int r, int qi, int gx
         // Some pixel of the quad is saturated: divide all four by max(1,|xi|) with the shared-reciprocal
         // fast path (x/1 is exact there too) under ONE range test for the quad; anything unusual
         // (zero / tiny / huge numerator, huge norm) takes IEEE division for the whole quad.
-        bool ok = big < 1e6f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) nr[k] = sqrtf(nr[k]);
+        bool ok = big < 1e12f;  // (big holds the largest squared norm)
 #pragma unroll
         for (int k = 0; k < 4; k++)
             ok = ok && fastdiv_nz_ok(x11[k]) && fastdiv_nz_ok(x12[k]) && fastdiv_nz_ok(x21[k]) && fastdiv_nz_ok(x22[k]);
