@@ -340,6 +340,8 @@ static int create_internal(faldoi_solver **out, int device, int w, int h, int me
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(tv_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
                  "cudaFuncSetAttribute") ||
+        !cuda_ok(cudaFuncSetAttribute(tv_tile2_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem) + 128),
+                 "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_TVL1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),
                  "cudaFuncSetAttribute") ||
         !cuda_ok(cudaFuncSetAttribute(nltv_tile_kernel<DATA_CSAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NlTileSmem) + 128),

@@ -58,6 +58,7 @@ struct Tile2Smem {
     float pl_[5][T2_PL_FLOATS];  // u1, u2, rho_c, Ix, Iy; row index = relative row + 1
     float red[2][T2_WARPS];
     unsigned long long bar;
+    unsigned item, pad_;  // dataflow grid: the work item this CTA took
     __device__ __forceinline__ float *ub(int k, int r) { return &ub_[k][(r + 2) * T2_PW]; }
     __device__ __forceinline__ float *xi(int k, int r) { return &xi_[k][(r + 2) * T2_PW]; }
     __device__ __forceinline__ float *pl(int k, int r) { return &pl_[k][(r + 1) * T2_PW]; }
@@ -249,24 +250,54 @@ struct T2Args {
     unsigned wait_val;                  // launches every stripe has been asked to complete before this one
 };
 
-__global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
+// Dataflow variant (FLOW): ONE grid runs `flow.iters` forced iterations = several launches' worth of tiles, without a
+// grid-wide barrier between them.  A CTA takes a work item from a ticket counter (launch-major, so every item it can
+// depend on has been taken by a CTA that is running or done: no deadlock whatever the dispatch order), and waits until
+// the 3x3 tiles around its own have completed the launch before - the only tiles whose output it reads and whose input
+// it overwrites - which they announce with a release store of their launch sequence number.  The tail of a launch
+// (2.2 waves of CTAs on a 270-row stripe) and the launch gap then overlap the next launch instead of idling the GPU.
+// Only forced modes (speculative blocks, stripes.inc): the exit test needs the whole frame's maximum.
+struct T2Flow {
+    unsigned *done;    // [B][nby][nbx]: sequence number + 1 of the last launch the tile has completed (monotone)
+    unsigned *ticket;  // work-item counter (monotone, never reset)
+    unsigned ticket0;  // its value when this grid starts
+    unsigned seq0;     // sequence number of this grid's first launch
+    int iters;         // iterations this grid runs: two per launch, the last launch the remainder
+    int nbx, nby;
+};
+
+template <bool FLOW>
+__device__ __forceinline__ void tv_tile2_body(const Tile2Maps &maps, const TvArgs &a, const T2Args &t2, int L, const T2Flow &flow) {
     // (no pointer arithmetic on the base: it would demote every access from LDS/STS to generic LD/ST)
     extern __shared__ __align__(1024) unsigned char smem_raw2[];
     Tile2Smem &S = *reinterpret_cast<Tile2Smem *>(smem_raw2);
-    const int b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+    int b, bx, by, nbx, nby, l = 0;
+    if (FLOW) {
+        if (tid == 0) S.item = atomicAdd(flow.ticket, 1u) - flow.ticket0;
+        __syncthreads();
+        nbx = flow.nbx, nby = flow.nby;
+        const unsigned ntile = (unsigned)(nbx * nby), per = ntile * (unsigned)a.g.B, item = S.item;
+        l = (int)(item / per);
+        const unsigned rem = item % per, t = rem % ntile;
+        b = (int)(rem / ntile);
+        by = (int)(t / (unsigned)nbx), bx = (int)(t % (unsigned)nbx);
+        L += l;
+    } else {
+        b = blockIdx.z, bx = blockIdx.x, by = blockIdx.y, nbx = gridDim.x, nby = gridDim.y;
+    }
     const int par0 = a.parity[b];
     const int it = 2 * L;  // first iteration of this launch
     // tile row of this CTA.  Stripe mode: the CTAs that produce a neighbour's halo rows (tile row 0; the last two tile
     // rows) are dispatched first, so that their rows -- and the signal that they are there -- cross NVLink while the
     // interior of the stripe is still being computed.
-    const int nby = gridDim.y;
-    int by = blockIdx.y;
     if (t2.boundary_first && nby >= 3) by = (by == 0) ? 0 : (by <= 2 ? nby - 3 + by : by - 2);
 
     // ---- what does this launch do for pair b?  (see the header comment) ----
     int mode, par_in = (par0 + L) & 1;
-    if (t2.force) {
+    if (FLOW) {
+        mode = (2 * l + 1 < flow.iters) ? T2_MODE_TWO : T2_MODE_ONE;
+    } else if (t2.force) {
         mode = t2.force;
     } else {
         unsigned char *st = t2.stat + (size_t)b * t2.stat_stride;
@@ -286,16 +317,32 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
                 mode = (it + 1 < a.max_iters) ? T2_MODE_TWO : T2_MODE_ONE;
             }
         }
-        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) st[L] = (mode == T2_MODE_TWO);
+        if (tid == 0 && bx == 0 && by == 0) st[L] = (mode == T2_MODE_TWO);
     }
     if (mode == T2_MODE_SKIP) return;
 
     const int w = a.g.w, h = a.g.h, pitch = a.g.pitch, hg = a.g.hg, yo = a.g.y_off;
-    const int x0 = blockIdx.x * T2_W, y0 = by * T2_H;
+    const int x0 = bx * T2_W, y0 = by * T2_H;
     const int rows = min(T2_H, h - y0);
     const size_t plane = a.g.plane, ks = (size_t)a.g.B * plane;
     float *out = a.state + (size_t)(par_in ^ 1) * a.set_stride + (size_t)b * plane;
 
+    const unsigned seq = flow.seq0 + (unsigned)l;  // FLOW: launches completed (by everybody) before this one
+    if (FLOW && l > 0 && wi == 0) {
+        // the launch before is in the same grid: wait for the tiles around this one (lanes 0..8 poll one tile each)
+        if (lane < 9) {
+            const int ny = by + lane / 3 - 1, nx = bx + lane % 3 - 1;
+            if (ny >= 0 && ny < nby && nx >= 0 && nx < nbx) {
+                const unsigned *q = flow.done + ((size_t)b * nby + ny) * nbx + nx;
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(q) : "memory");
+                } while ((int)(v - seq) < 0);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) __threadfence();
+    }
     if (tid == 0) {
         // Stripe mode: a CTA next to a stripe boundary reads halo rows the neighbour GPU stores, and overwrites halo
         // rows the neighbour reads.  Both are safe once the neighbour's boundary CTAs of the launch before have
@@ -304,16 +351,18 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
         if (t2.boundary_first) {
             const unsigned *f = (by == 0) ? t2.wait_up : (by >= nby - 2 ? t2.wait_dn : nullptr);
             const unsigned *f2 = (by == 0 && by >= nby - 2) ? t2.wait_dn : nullptr;  // a stripe of one or two tile rows
+            const unsigned want = t2.wait_val + (unsigned)l;
             for (int k = 0; k < 2; k++) {
                 const unsigned *q = k ? f2 : f;
                 if (!q) continue;
                 unsigned v;
                 do {
                     asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(q) : "memory");
-                } while (v < t2.wait_val);
+                } while (v < want);
             }
-            asm volatile("fence.proxy.async;\n" ::: "memory");  // the TMA loads below must see what the flag announced
         }
+        // the TMA loads below must see what the flags announced
+        if (FLOW || t2.boundary_first) asm volatile("fence.proxy.async;\n" ::: "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&S.bar)), "r"((unsigned)T2_TX_BYTES) : "memory");
@@ -429,17 +478,32 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
         __syncthreads();
         if (tid == 0) {
             __threadfence_system();
+            // FLOW: launches of one grid overlap, so each has its own pair of arrival counters (the last arrival
+            // resets them) and the flag is raised with a max: a later launch's signal may overtake an earlier one's
+            unsigned *cnt = t2.sig_cnt + (FLOW ? 8 + 2 * l : 0);
             if (by == 0 && t2.sig_up) {
-                const unsigned n = atomicAdd(&t2.sig_cnt[0], 1u) + 1u;
-                if (n % gridDim.x == 0) {
+                const unsigned n = atomicAdd(&cnt[0], 1u) + 1u;
+                if (FLOW) {
+                    if (n == (unsigned)nbx) {
+                        cnt[0] = 0;
+                        __threadfence_system();
+                        asm volatile("red.release.sys.global.max.u32 [%0], %1;\n" ::"l"(t2.sig_up), "r"(t2.wait_val + (unsigned)l + 1u) : "memory");
+                    }
+                } else if (n % nbx == 0) {
                     __threadfence_system();
-                    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(t2.sig_up), "r"(n / gridDim.x) : "memory");
+                    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(t2.sig_up), "r"(n / nbx) : "memory");
                 }
             }
             if (by >= nby - 2 && t2.sig_dn) {
-                const unsigned n = atomicAdd(&t2.sig_cnt[1], 1u) + 1u;
-                const unsigned per_launch = min(2, nby) * gridDim.x;
-                if (n % per_launch == 0) {
+                const unsigned n = atomicAdd(&cnt[1], 1u) + 1u;
+                const unsigned per_launch = min(2, nby) * nbx;
+                if (FLOW) {
+                    if (n == per_launch) {
+                        cnt[1] = 0;
+                        __threadfence_system();
+                        asm volatile("red.release.sys.global.max.u32 [%0], %1;\n" ::"l"(t2.sig_dn), "r"(t2.wait_val + (unsigned)l + 1u) : "memory");
+                    }
+                } else if (n % per_launch == 0) {
                     __threadfence_system();
                     asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(t2.sig_dn), "r"(n / per_launch) : "memory");
                 }
@@ -469,7 +533,21 @@ __global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(co
         } else {
             atomicMax(e, __float_as_uint(mB));
         }
+        if (FLOW) {
+            // every thread's stores precede the barrier above: publish "this tile has completed launch seq"
+            asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flow.done + ((size_t)b * nby + by) * nbx + bx), "r"(seq + 1u) : "memory");
+        }
     }
+}
+
+// one launch = two iterations of every tile, grid (tiles x, tiles y, pairs)
+__global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L) {
+    tv_tile2_body<false>(maps, a, t2, L, T2Flow{});
+}
+// the dataflow grid: ceil(flow.iters / 2) launches' worth of tiles, 1-D grid of that many x tiles x pairs CTAs
+__global__ void __launch_bounds__(T2_THREADS, FALDOI_T2_CTAS) tv_tile2_flow_kernel(const __grid_constant__ Tile2Maps maps, TvArgs a, T2Args t2, int L,
+                                                                                    T2Flow flow) {
+    tv_tile2_body<true>(maps, a, t2, L, flow);
 }
 
 }  // namespace faldoi

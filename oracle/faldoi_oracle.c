@@ -11,8 +11,16 @@
 #include "faldoi_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* optional per-iteration error trace of fo_tvl2 (tools/stripes_policy.py): "warp iteration err" lines */
+static FILE *fo_err_trace = NULL;
+void fo_set_err_trace(const char *path) {
+    if (fo_err_trace) fclose(fo_err_trace);
+    fo_err_trace = path ? fopen(path, "w") : NULL;
+}
 
 #define GRAD_IS_ZERO 1E-8 /* src/parameters.h:45 (a double literal: comparisons promote) */
 
@@ -352,6 +360,7 @@ void fo_tvl2(const float *I0, const float *I1, float *u1, float *u2, float *xi11
             for (int i = 1; i < n; i++)
                 if (uN[i] > mx) mx = uN[i];
             err = mx;
+            if (fo_err_trace) fprintf(fo_err_trace, "%d %d %.9g\n", wp, it, err);
         }
         if (log && wp < FO_MAX_WARPS) {
             log->iters[wp] = it;

@@ -47,6 +47,8 @@ void fo_preprocess(const float *i0, const float *i1, const float *im1, int pd, i
 void fo_default_params(fo_params *p);
 
 /* ---- solvers.  u1,u2 (and xi / chi) are updated in place ---- */
+/* test tooling: write "warp iteration err" lines of every fo_tvl2 iteration to `path` (NULL: stop) */
+void fo_set_err_trace(const char *path);
 void fo_tvl2(const float *I0, const float *I1, float *u1, float *u2, float *xi11, float *xi12, float *xi21,
              float *xi22, float lambda, float theta, float tau, float tol, int w, int h, int warps,
              int max_iter, fo_log *log);

@@ -64,10 +64,11 @@ def test_sharding_logic_gloo_world2(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("sync", ["events", "memops"])
-@pytest.mark.parametrize("w,h,n", [(160, 70, 2), (160, 70, 3), (96, 33, 4), (300, 131, 5)])
+@pytest.mark.parametrize("w,h,n", [(160, 70, 1), (300, 131, 1), (160, 70, 2), (160, 70, 3), (96, 33, 4), (300, 131, 5)])
 def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n, sync, monkeypatch):
-    """All stripes on device 0: exercises halo rows, peer stores, the cross-stripe ordering (events + host
-    barrier, or stream memory operations) and the global error gather without needing several GPUs."""
+    """All stripes on device 0: exercises halo rows, peer stores, the cross-stripe ordering and the global error
+    gather without needing several GPUs.  n = 1 runs every speculative block as ONE dataflow grid (tiles of
+    successive launches waiting for each other); stripes that share a GPU get one grid per launch."""
     monkeypatch.setenv("FALDOI_STRIPES_SYNC", sync)
     I0, I1, _, u0, _ = synthetic_pair(w, h, seed=w * 7 + h + n)
     p = fb.default_params(0, warps=3)
@@ -84,15 +85,17 @@ def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n, sync, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_striped_4k_equals_whole_frame(fb):
+@pytest.mark.parametrize("nstripes", [1, 3])
+def test_striped_4k_equals_whole_frame(fb, nstripes):
     """The shape the stripes exist for: a 3840x2160 pair in 3 stripes (device 0, or one per GPU when there are
-    several) against the whole-frame solve, one warp."""
+    several) against the whole-frame solve, one warp; and as a single stripe = dataflow grids of up to 32
+    launches over 7680 tiles."""
     w, h = 3840, 2160
     I0, I1, _, u0, _ = synthetic_pair(w, h, seed=9)
     p = fb.default_params(0, warps=1)
     whole, _, its, errs = fb.global_solve(0, I0, I1, u0, params=p)
     ndev = fb.device_count()
-    g = fb.Stripes(w, h, [k % ndev for k in range(3)])
+    g = fb.Stripes(w, h, [k % ndev for k in range(nstripes)])
     g.upload(I0, I1, u0)
     g.run(p)
     u, log = g.download()
