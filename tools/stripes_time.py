@@ -39,7 +39,7 @@ def run(nstripes, tol=None, reps=3):
 
 
 one = run(1)
-print("1 stripe: %.2f ms, %d iterations, %d kernel launches" % one[:3])
+print("1 stripe: %.2f ms, %d kernel launches, %d iterations" % one[:3])
 if n > 1:
     many = run(n)
     print("%d stripes: %.2f ms (%.2fx, efficiency %.3f), %d kernel launches, bit-identical: %s"
