@@ -63,13 +63,11 @@ def test_sharding_logic_gloo_world2(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sync", ["events", "memops"])
 @pytest.mark.parametrize("w,h,n", [(160, 70, 1), (300, 131, 1), (160, 70, 2), (160, 70, 3), (96, 33, 4), (300, 131, 5)])
-def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n, sync, monkeypatch):
+def test_striped_equals_whole_frame_one_gpu(fb, po, w, h, n):
     """All stripes on device 0: exercises halo rows, peer stores, the cross-stripe ordering and the global error
     gather without needing several GPUs.  n = 1 runs every speculative block as ONE dataflow grid (tiles of
     successive launches waiting for each other); stripes that share a GPU get one grid per launch."""
-    monkeypatch.setenv("FALDOI_STRIPES_SYNC", sync)
     I0, I1, _, u0, _ = synthetic_pair(w, h, seed=w * 7 + h + n)
     p = fb.default_params(0, warps=3)
     whole, _, its, errs = fb.global_solve(0, I0, I1, u0, params=p)
@@ -105,10 +103,8 @@ def test_striped_4k_equals_whole_frame(fb, nstripes):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sync", ["events", "memops"])
-def test_striped_across_gpus(fb, sync, monkeypatch):
+def test_striped_across_gpus(fb):
     """With >= 2 GPUs: one stripe per GPU, NVLink peer stores."""
-    monkeypatch.setenv("FALDOI_STRIPES_SYNC", sync)
     n = min(fb.device_count(), 8)
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
